@@ -1,0 +1,713 @@
+/*
+ * altair_oracle.c -- CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ * See altair_oracle.h for scope, reference citations and the "parity unpinned" statement.
+ * Build: see oracle/Makefile (-ffp-contract=off is REQUIRED: every fused multiply-add in
+ * the arithmetic contract is written explicitly).
+ */
+#define _GNU_SOURCE
+#include "altair_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define EV_WALL 1
+#define EV_EDGE 2
+#define EV_EXIT 3
+#define PI_D 3.14159265358979323846
+
+/* ------------------------------------------------------------------ scene constants */
+typedef struct {
+    double R1, R2, R1sq, R2sq, zc, T2, cth, sth, H, exit_z;
+    int lambertian, brdf_kind, max_bounces, count_all;
+} geom;
+
+typedef struct { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s; } consts_f;
+typedef struct { double rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s; } consts_d;
+
+static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
+    if (!(sc->r_inner > 0) || !(sc->r_outer >= sc->r_inner) || !(sc->world_half > sc->r_outer)) return -1;
+    if (!(sc->theta_max_deg > 90.0) || !(sc->theta_max_deg < 180.0)) return -1;
+    if (sc->max_bounces < 1) return -1;
+    double th = sc->theta_max_deg * PI_D / 180.0;
+    g->R1 = sc->r_inner; g->R2 = sc->r_outer;
+    g->R1sq = g->R1 * g->R1; g->R2sq = g->R2 * g->R2;
+    g->cth = cos(th); g->sth = sin(th);
+    g->zc = g->R1 * g->cth;
+    double t = g->sth / g->cth;
+    g->T2 = t * t;
+    g->H = sc->world_half; g->exit_z = sc->exit_z;
+    g->lambertian = sc->lambertian; g->brdf_kind = sc->brdf_kind;
+    g->max_bounces = sc->max_bounces; g->count_all = sc->count_all_status;
+    double ps = 0.0, bs = 0.0;
+    if (sc->brdf_kind == 1) {          /* nonLambertianFlux.C:156-159: normalise (spec,diff) */
+        double sum = sc->brdf_param[1] + sc->brdf_param[2];
+        if (!(sum > 0)) return -1;
+        ps = sc->brdf_param[1] / sum;
+        bs = sc->brdf_param[0] * PI_D / 6.0;
+    } else if (sc->brdf_kind != 0) return -1;
+    kd->rho = sc->reflectance; kd->sigma = sc->roughness_rad;
+    kd->two_r1 = 2.0 * g->R1; kd->neg_inv_r1 = -1.0 / g->R1; kd->nr_c = -0.5 / g->R1sq;
+    kd->zc = g->zc; kd->p_spec = ps; kd->brdf_s = bs;
+    kf->rho = (float)kd->rho; kf->sigma = (float)kd->sigma; kf->two_r1 = (float)kd->two_r1;
+    kf->neg_inv_r1 = (float)kd->neg_inv_r1; kf->nr_c = (float)kd->nr_c; kf->zc = (float)kd->zc;
+    kf->p_spec = (float)kd->p_spec; kf->brdf_s = (float)kd->brdf_s;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ double slow path
+ * (port crossing, conical port edge, world box) -- IEEE + - * / sqrt only, no contraction,
+ * so the kernels' double slow path reproduces it bit for bit.  SURVEY.md appendix A.1/A.3. */
+static void box_exit(const geom* g, const double* x, const double* d, double* e) {
+    double t = INFINITY;
+    for (int i = 0; i < 3; i++) {
+        double ti;
+        if (d[i] > 0.0) ti = (g->H - x[i]) / d[i];
+        else if (d[i] < 0.0) ti = (-g->H - x[i]) / d[i];
+        else continue;
+        if (ti < t) t = ti;
+    }
+    for (int i = 0; i < 3; i++) e[i] = x[i] + t * d[i];
+}
+
+/* x0 = S1 crossing inside the opening, heading outward.  EDGE(q) or EXIT(e). */
+static int cap_crossing(const geom* g, const double* x0, const double* d, double* out) {
+    double A = (d[0] * d[0] + d[1] * d[1]) - g->T2 * (d[2] * d[2]);
+    double B = (x0[0] * d[0] + x0[1] * d[1]) - g->T2 * (x0[2] * d[2]);
+    double C = (x0[0] * x0[0] + x0[1] * x0[1]) - g->T2 * (x0[2] * x0[2]);
+    double disc = B * B - A * C;
+    double s = 0.0;
+    int have = 0;
+    if (disc >= 0.0) {
+        double sq = sqrt(disc);
+        if (B > 0.0) { double den = B + sq; if (den > 0.0) { s = -C / den; have = 1; } }
+        else if (A > 0.0) { s = (sq - B) / A; have = 1; }
+    }
+    if (have && s > 0.0) {
+        double q[3] = {x0[0] + s * d[0], x0[1] + s * d[1], x0[2] + s * d[2]};
+        if (q[2] < 0.0) {
+            double r2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+            if (r2 <= g->R2sq) { out[0] = q[0]; out[1] = q[1]; out[2] = q[2]; return EV_EDGE; }
+        }
+    }
+    box_exit(g, x0, d, out);
+    return EV_EXIT;
+}
+
+/* q on the conical port edge, d heading into the opening.  WALL / EDGE / EXIT. */
+static int from_edge(const geom* g, const double* q, const double* d, double* out) {
+    double A = (d[0] * d[0] + d[1] * d[1]) - g->T2 * (d[2] * d[2]);
+    double B = (q[0] * d[0] + q[1] * d[1]) - g->T2 * (q[2] * d[2]);
+    double s_c = INFINITY, xc[3] = {0, 0, 0};
+    if (A > 0.0 && B < 0.0) {
+        double s = (-2.0 * B) / A;
+        double x[3] = {q[0] + s * d[0], q[1] + s * d[1], q[2] + s * d[2]};
+        if (x[2] < 0.0) {
+            double r2 = (x[0] * x[0] + x[1] * x[1]) + x[2] * x[2];
+            if (r2 >= g->R1sq && r2 <= g->R2sq) { s_c = s; xc[0] = x[0]; xc[1] = x[1]; xc[2] = x[2]; }
+        }
+    }
+    double s_in = INFINITY;
+    double b = (q[0] * d[0] + q[1] * d[1]) + q[2] * d[2];
+    double c0 = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) - g->R1sq;
+    if (b < 0.0) {
+        if (c0 > 0.0) { double disc = b * b - c0; if (disc > 0.0) s_in = -b - sqrt(disc); }
+        else s_in = 0.0;
+    }
+    if (s_c < s_in) { out[0] = xc[0]; out[1] = xc[1]; out[2] = xc[2]; return EV_EDGE; }
+    if (s_in < INFINITY) {
+        double xin[3] = {q[0] + s_in * d[0], q[1] + s_in * d[1], q[2] + s_in * d[2]};
+        double bb = (xin[0] * d[0] + xin[1] * d[1]) + xin[2] * d[2];
+        double cc = ((xin[0] * xin[0] + xin[1] * xin[1]) + xin[2] * xin[2]) - g->R1sq;
+        double disc = bb * bb - cc;
+        if (disc < 0.0) disc = 0.0;
+        double t = sqrt(disc) - bb;
+        double h[3] = {xin[0] + t * d[0], xin[1] + t * d[1], xin[2] + t * d[2]};
+        double sc = g->R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+        h[0] *= sc; h[1] *= sc; h[2] *= sc;
+        if (h[2] >= g->zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+        return cap_crossing(g, h, d, out);
+    }
+    box_exit(g, q, d, out);
+    return EV_EXIT;
+}
+
+/* Normal of the conical edge at q, pointing into the opening (theta-hat at theta_max). */
+static void edge_normal(const geom* g, const double* q, double* n) {
+    double rho = sqrt(q[0] * q[0] + q[1] * q[1]);
+    if (rho > 0.0) { n[0] = g->cth * (q[0] / rho); n[1] = g->cth * (q[1] / rho); }
+    else { n[0] = 0.0; n[1] = 0.0; }
+    n[2] = -g->sth;
+}
+
+/* First event of a ray launched at p0 (inside the cavity) along dir (appendix A.2). */
+static int launch(const geom* g, const double* p0, const double* dir, double* d0, double* out) {
+    double m = sqrt((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+    if (!(m > 0.0)) return -1;
+    for (int i = 0; i < 3; i++) d0[i] = dir[i] / m;
+    double b = (p0[0] * d0[0] + p0[1] * d0[1]) + p0[2] * d0[2];
+    double c0 = ((p0[0] * p0[0] + p0[1] * p0[1]) + p0[2] * p0[2]) - g->R1sq;
+    if (!(c0 < 0.0)) return -1;
+    double t = sqrt(b * b - c0) - b;
+    double h[3] = {p0[0] + t * d0[0], p0[1] + t * d0[1], p0[2] + t * d0[2]};
+    double sc = g->R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+    h[0] *= sc; h[1] *= sc; h[2] *= sc;
+    if (h[2] >= g->zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+    return cap_crossing(g, h, d0, out);
+}
+
+/* ------------------------------------------------------------------ f32 primitives */
+static inline float as_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t as_u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+static inline void sincos_poly_f32(float x, int q, float* s, float* c) {
+    float x2 = x * x;
+    float ps = fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, x2, -1.6666654611e-1f);
+    float sn = fmaf(x * x2, ps, x);
+    float pc = fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, x2, 4.166664568298827e-2f);
+    float cs = fmaf(x2 * x2, pc, fmaf(x2, -0.5f, 1.0f));
+    switch (q & 3) {
+        case 0: *s = sn;  *c = cs;  break;
+        case 1: *s = cs;  *c = -sn; break;
+        case 2: *s = -sn; *c = -cs; break;
+        default: *s = -cs; *c = sn; break;
+    }
+}
+
+void orc_sincos2pi_f32(float u, float* s, float* c) {
+    float q = rintf(u * 4.0f);
+    float r = fmaf(q, -0.25f, u);
+    sincos_poly_f32(r * 6.2831855f, (int)q, s, c);
+}
+
+void orc_sincos_f32(float x, float* s, float* c) {
+    float q = rintf(x * 0.63661975f);
+    float r = fmaf(q, -1.5707964f, x);
+    r = fmaf(q, 4.3711388e-8f, r);
+    sincos_poly_f32(r, (int)q, s, c);
+}
+
+float orc_log_f32(float x) {
+    uint32_t b = as_u(x);
+    int e = (int)(b >> 23) - 127;
+    float m = as_f((b & 0x007fffffu) | 0x3f800000u);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    float z = m - 1.0f;
+    float z2 = z * z;
+    float p = 7.0376836292e-2f;
+    p = fmaf(p, z, -1.1514610310e-1f);
+    p = fmaf(p, z, 1.1676998740e-1f);
+    p = fmaf(p, z, -1.2420140846e-1f);
+    p = fmaf(p, z, 1.4249322787e-1f);
+    p = fmaf(p, z, -1.6668057665e-1f);
+    p = fmaf(p, z, 2.0000714765e-1f);
+    p = fmaf(p, z, -2.4999993993e-1f);
+    p = fmaf(p, z, 3.3333331174e-1f);
+    float fe = (float)e;
+    float y = (z * z2) * p;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z2, -0.5f, y);
+    float r = z + y;
+    return fmaf(fe, 0.693359375f, r);
+}
+
+static inline void sincos2pi_d(double u, double* s, double* c) { double x = 2.0 * PI_D * u; *s = sin(x); *c = cos(x); }
+static inline void sincos_d(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+
+/* ------------------------------------------------------------------ Philox + draws */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static inline float u01(uint32_t w) { return (float)(w >> 8) * 0x1p-24f; }
+
+void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, 0u};
+    uint32_t a[4], b[4];
+    orc_philox4x32_10(ctr, key, a);
+    ctr[3] = 1u;
+    orc_philox4x32_10(ctr, key, b);
+    out[0] = u01(a[0]); out[1] = u01(a[1]); out[2] = u01(a[2]); out[3] = u01(a[3]);
+    out[4] = u01(b[0]);
+    float u1 = (float)((b[1] >> 8) + 1u) * 0x1p-24f;       /* (0,1] */
+    float rad = sqrtf(-2.0f * orc_log_f32(u1));
+    float s, c;
+    orc_sincos2pi_f32(u01(b[2]), &s, &c);
+    out[5] = rad * c; out[6] = rad * s;
+    out[7] = u01(b[3]);
+}
+
+/* ------------------------------------------------------------------ the two instantiations */
+#define REAL float
+#define SUF(n) n##_f
+#define RC(x) x##f
+#define FMA(a, b, c) fmaf(a, b, c)
+#define SQRT(x) sqrtf(x)
+#define FABS(x) fabsf(x)
+#define COPYSIGN(a, b) copysignf(a, b)
+#define SINCOS2PI(u, s, c) orc_sincos2pi_f32(u, s, c)
+#define SINCOS(x, s, c) orc_sincos_f32(x, s, c)
+#include "oracle_core.inc"
+#undef REAL
+#undef SUF
+#undef RC
+#undef FMA
+#undef SQRT
+#undef FABS
+#undef COPYSIGN
+#undef SINCOS2PI
+#undef SINCOS
+
+#define REAL double
+#define SUF(n) n##_d
+#define RC(x) x
+#define FMA(a, b, c) ((a) * (b) + (c))
+#define SQRT(x) sqrt(x)
+#define FABS(x) fabs(x)
+#define COPYSIGN(a, b) copysign(a, b)
+#define SINCOS2PI(u, s, c) sincos2pi_d(u, s, c)
+#define SINCOS(x, s, c) sincos_d(x, s, c)
+#include "oracle_core.inc"
+#undef REAL
+#undef SUF
+#undef RC
+#undef FMA
+#undef SQRT
+#undef FABS
+#undef COPYSIGN
+#undef SINCOS2PI
+#undef SINCOS
+
+/* ------------------------------------------------------------------ per-ray drivers */
+typedef struct { const float* tape; uint64_t n_rec; } tape_src;   /* tape == NULL -> Philox */
+
+typedef struct { double pos[3], dir[3]; uint32_t n_hits; uint32_t status; } result_d;
+
+__attribute__((target_clones("arch=haswell","default")))
+static void run_ray(const geom* g, const consts_f* kf, const consts_d* kd, int prec,
+                    int kind0, const double* x0, const double* d0,
+                    uint64_t seed, uint64_t ray_id, const tape_src* ts,
+                    orc_record* rec, result_d* rd, float* tape_out, uint64_t* tape_n) {
+    float dr[ORC_DRAWS_PER_HIT];
+    int st;
+    uint32_t k = 0;
+    if (prec == ORC_F32) {
+        state_f s;
+        st = start_f(g, kf, &s, kind0, x0, d0);
+        while (!st) {
+            if (ts && ts->tape) {
+                if (k >= ts->n_rec) { st = ORC_TAPE_END; break; }
+                memcpy(dr, ts->tape + 8 * (uint64_t)k, sizeof dr);
+            } else orc_draws(seed, ray_id, k, dr);
+            if (tape_out) memcpy(tape_out + 8 * (uint64_t)k, dr, sizeof dr);
+            k++;
+            st = bounce_f(g, kf, &s, dr);
+        }
+        if (tape_n) *tape_n = k;
+        if (rec) {
+            for (int i = 0; i < 3; i++) { rec->pos[i] = s.pos[i]; rec->dir[i] = s.dir[i]; }
+            rec->n_hits = s.n_hits; rec->status = (uint32_t)st;
+        }
+        if (rd) {
+            for (int i = 0; i < 3; i++) { rd->pos[i] = s.pos[i]; rd->dir[i] = s.dir[i]; }
+            rd->n_hits = s.n_hits; rd->status = (uint32_t)st;
+        }
+    } else {
+        state_d s;
+        st = start_d(g, kd, &s, kind0, x0, d0);
+        while (!st) {
+            if (ts && ts->tape) {
+                if (k >= ts->n_rec) { st = ORC_TAPE_END; break; }
+                memcpy(dr, ts->tape + 8 * (uint64_t)k, sizeof dr);
+            } else orc_draws(seed, ray_id, k, dr);
+            k++;
+            st = bounce_d(g, kd, &s, dr);
+        }
+        if (tape_n) *tape_n = k;
+        if (rec) {
+            for (int i = 0; i < 3; i++) { rec->pos[i] = (float)s.pos[i]; rec->dir[i] = (float)s.dir[i]; }
+            rec->n_hits = s.n_hits; rec->status = (uint32_t)st;
+        }
+        if (rd) {
+            for (int i = 0; i < 3; i++) { rd->pos[i] = s.pos[i]; rd->dir[i] = s.dir[i]; }
+            rd->n_hits = s.n_hits; rd->status = (uint32_t)st;
+        }
+    }
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static int pick_threads(int n_threads) {
+#ifdef _OPENMP
+    return n_threads <= 0 ? omp_get_max_threads() : n_threads;
+#else
+    (void)n_threads; return 1;
+#endif
+}
+
+static int port_flag_g(const geom* g, const float* pos, uint32_t status) {
+    if (!(g->count_all || status == ORC_EXITED)) return 0;
+    return pos[2] < (float)g->exit_z;
+}
+
+int orc_port_flag(const orc_scene* sc, const orc_record* r) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    return port_flag_g(&g, r->pos, r->status);
+}
+
+static void add_stats(const geom* g, const orc_record* r, orc_stats* s) {
+    s->n_rays += 1; s->n_bounces += r->n_hits;
+    if (r->status == ORC_EXITED) s->n_exited += 1;
+    else if (r->status == ORC_ABSORBED) s->n_absorbed += 1;
+    else if (r->status == ORC_SUSPENDED) s->n_suspended += 1;
+    if (port_flag_g(g, r->pos, r->status)) s->n_exit_port += 1;
+}
+
+int orc_trace(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+              int prec, orc_record* rec, orc_stats* stats, int n_threads) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    double d0[3], x0[3];
+    int kind0 = launch(&g, src->pos, src->dir, d0, x0);
+    if (kind0 < 0) return -2;
+    int nt = pick_threads(n_threads);
+    orc_stats tot; memset(&tot, 0, sizeof tot);
+    #pragma omp parallel num_threads(nt)
+    {
+        orc_stats loc; memset(&loc, 0, sizeof loc);
+        #pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            orc_record r;
+            run_ray(&g, &kf, &kd, prec, kind0, x0, d0, seed, ray_id0 + (uint64_t)i, NULL, &r, NULL, NULL, NULL);
+            if (rec) rec[i] = r;
+            add_stats(&g, &r, &loc);
+        }
+        #pragma omp critical
+        {
+            tot.n_rays += loc.n_rays; tot.n_exited += loc.n_exited; tot.n_exit_port += loc.n_exit_port;
+            tot.n_absorbed += loc.n_absorbed; tot.n_suspended += loc.n_suspended; tot.n_bounces += loc.n_bounces;
+        }
+    }
+    if (stats) *stats = tot;
+    return 0;
+}
+
+int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                  double* pos, double* dir, uint32_t* n_hits, uint8_t* status, int n_threads) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    double d0[3], x0[3];
+    int kind0 = launch(&g, src->pos, src->dir, d0, x0);
+    if (kind0 < 0) return -2;
+    int nt = pick_threads(n_threads);
+    #pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        result_d r;
+        run_ray(&g, &kf, &kd, ORC_F64, kind0, x0, d0, seed, ray_id0 + (uint64_t)i, NULL, NULL, &r, NULL, NULL);
+        for (int j = 0; j < 3; j++) { if (pos) pos[3 * i + j] = r.pos[j]; if (dir) dir[3 * i + j] = r.dir[j]; }
+        if (n_hits) n_hits[i] = r.n_hits;
+        if (status) status[i] = (uint8_t)r.status;
+    }
+    return 0;
+}
+
+int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
+               uint64_t n, int prec, orc_record* rec) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    int bad = 0;
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        double d0[3], x0[3];
+        int kind0 = launch(&g, ray0 + 6 * i, ray0 + 6 * i + 3, d0, x0);
+        if (kind0 < 0) { bad = 1; memset(&rec[i], 0, sizeof rec[i]); continue; }
+        tape_src ts = {tape + 8 * tape_off[i], tape_off[i + 1] - tape_off[i]};
+        run_ray(&g, &kf, &kd, prec, kind0, x0, d0, 0, 0, &ts, &rec[i], NULL, NULL, NULL);
+    }
+    return bad ? -2 : 0;
+}
+
+int64_t orc_make_tape(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n,
+                      uint64_t seed, float* tape, uint64_t cap_records, uint64_t* tape_off) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    double d0[3], x0[3];
+    int kind0 = launch(&g, src->pos, src->dir, d0, x0);
+    if (kind0 < 0) return -2;
+    /* pass 1: lengths */
+    uint64_t total = 0;
+    tape_off[0] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t cnt = 0;
+        run_ray(&g, &kf, &kd, ORC_F32, kind0, x0, d0, seed, ray_id0 + i, NULL, NULL, NULL, NULL, &cnt);
+        total += cnt;
+        tape_off[i + 1] = total;
+    }
+    if (!tape) return (int64_t)total;            /* length query: tape_off is filled */
+    if (total > cap_records) return -3;
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        uint64_t cnt = 0;
+        run_ray(&g, &kf, &kd, ORC_F32, kind0, x0, d0, seed, ray_id0 + (uint64_t)i, NULL, NULL, NULL,
+                tape + 8 * tape_off[i], &cnt);
+    }
+    return (int64_t)total;
+}
+
+/* ------------------------------------------------------------------ map stage */
+void orc_detector_pose(double theta_deg, double phi_deg, double radius, double pos[3], double nrm[3]) {
+    /* fluxAtObserverFast.C:61-80, literal */
+    double theta_rad = theta_deg * M_PI / 180.0;
+    double phi_rad = phi_deg * M_PI / 180.0;
+    double x = radius * sin(theta_rad) * cos(phi_rad);
+    double y = radius * sin(theta_rad) * sin(phi_rad);
+    double z = -100.0 - radius * cos(theta_rad);
+    double dx = x - 0, dy = y - 0, dz = z - (-100.0);
+    double mag = sqrt(dx * dx + dy * dy + dz * dz);
+    pos[0] = x; pos[1] = y; pos[2] = z;
+    nrm[0] = -dy / mag; nrm[1] = dx / mag; nrm[2] = dz / mag;
+}
+
+int orc_detector_hit(const double pos[3], const double nrm[3], double width,
+                     const double lastPoint[3], const double direction[3]) {
+    /* fluxAtObserverFast.C:82-119, literal */
+    double nx = nrm[0], ny = nrm[1], nz = nrm[2];
+    double dot = direction[0] * nx + direction[1] * ny + direction[2] * nz;
+    if (fabs(dot) < 1e-10) return 0;
+    double dx = lastPoint[0] - pos[0], dy = lastPoint[1] - pos[1], dz = lastPoint[2] - pos[2];
+    double t = -(dx * nx + dy * ny + dz * nz) / dot;
+    double ix = lastPoint[0] + direction[0] * t, iy = lastPoint[1] + direction[1] * t, iz = lastPoint[2] + direction[2] * t;
+    double rx = ix - pos[0], ry = iy - pos[1], rz = iz - pos[2];
+    double ux = ny * rz - nz * ry, uy = nz * rx - nx * rz, uz = nx * ry - ny * rx;
+    double r2 = ux * ux + uy * uy + uz * uz;
+    return r2 <= (width / 2) * (width / 2);
+}
+
+int32_t orc_direction_bin(const orc_map_spec* map, const float d[3]) {
+    if (!(d[2] < 0.0f)) return -1;
+    double c = -(double)d[2];
+    if (c > 1.0) c = 1.0;
+    double th = acos(c) * (180.0 / PI_D);
+    double ph = atan2((double)d[1], (double)d[0]) * (180.0 / PI_D);
+    if (ph < 0.0) ph += 360.0;
+    int i = (int)floor(th / (90.0 / map->n_theta));
+    int j = (int)floor(ph / (360.0 / map->n_phi));
+    if (i > map->n_theta - 1) i = map->n_theta - 1;
+    if (j > map->n_phi - 1) j = map->n_phi - 1;
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    return i * map->n_phi + j;
+}
+
+typedef struct { float* rs; float* pz; float* st; float* ct; float* cp; float* sp; float w2; } map_tab_f;
+
+static void make_tab_f(const orc_map_spec* map, map_tab_f* t) {
+    int nt = map->n_theta, np = map->n_phi;
+    t->rs = malloc(sizeof(float) * nt); t->pz = malloc(sizeof(float) * nt);
+    t->st = malloc(sizeof(float) * nt); t->ct = malloc(sizeof(float) * nt);
+    t->cp = malloc(sizeof(float) * np); t->sp = malloc(sizeof(float) * np);
+    for (int i = 0; i < nt; i++) {
+        double th = (i + 0.5) * 90.0 / nt * PI_D / 180.0;
+        t->st[i] = (float)sin(th); t->ct[i] = (float)cos(th);
+        t->rs[i] = (float)(map->det_radius * sin(th));
+        t->pz[i] = (float)(-100.0 - map->det_radius * cos(th));
+    }
+    for (int j = 0; j < np; j++) {
+        double ph = (j + 0.5) * 360.0 / np * PI_D / 180.0;
+        t->cp[j] = (float)cos(ph); t->sp[j] = (float)sin(ph);
+    }
+    double hw = map->det_width / 2;
+    t->w2 = (float)(hw * hw);
+}
+static void free_tab_f(map_tab_f* t) { free(t->rs); free(t->pz); free(t->st); free(t->ct); free(t->cp); free(t->sp); }
+
+/* the kernels' division-free f32 line-disk test (DESIGN.md "map stage") */
+static inline int line_hit_f32(const map_tab_f* t, int i, int j, const float* L, const float* v) {
+    float p0 = t->rs[i] * t->cp[j], p1 = t->rs[i] * t->sp[j], p2 = t->pz[i];
+    float n0 = -(t->st[i] * t->sp[j]), n1 = t->st[i] * t->cp[j], n2 = -t->ct[i];
+    float dot = fmaf(v[0], n0, fmaf(v[1], n1, v[2] * n2));
+    if (fabsf(dot) < 1e-10f) return 0;
+    float d0 = L[0] - p0, d1 = L[1] - p1, d2 = L[2] - p2;
+    float num = fmaf(d0, n0, fmaf(d1, n1, d2 * n2));
+    float q0 = fmaf(dot, d0, -(num * v[0]));
+    float q1 = fmaf(dot, d1, -(num * v[1]));
+    float q2 = fmaf(dot, d2, -(num * v[2]));
+    float r2 = fmaf(q0, q0, fmaf(q1, q1, q2 * q2));
+    return r2 <= t->w2 * (dot * dot);
+}
+
+int orc_map_records(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n,
+                    int prec, uint64_t* counts, int n_threads) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    int nt = map->n_theta, np = map->n_phi, nb = nt * np;
+    if (nt < 1 || np < 1) return -1;
+    if (map->map_mode == ORC_MAP_DIRECTION) {
+        for (uint64_t r = 0; r < n; r++) {
+            if (!port_flag_g(&g, rec[r].pos, rec[r].status)) continue;
+            int32_t b = orc_direction_bin(map, rec[r].dir);
+            if (b >= 0) counts[b] += 1;
+        }
+        return 0;
+    }
+    if (map->map_mode != ORC_MAP_LINE && map->map_mode != ORC_MAP_TRACEONCE_COMPAT) return -1;
+    int compat = map->map_mode == ORC_MAP_TRACEONCE_COMPAT;
+    map_tab_f tab; make_tab_f(map, &tab);
+    double* dp = malloc(sizeof(double) * 6 * nb);
+    for (int i = 0; i < nt; i++)
+        for (int j = 0; j < np; j++)
+            orc_detector_pose((i + 0.5) * 90.0 / nt, (j + 0.5) * 360.0 / np, map->det_radius,
+                              dp + 6 * (i * np + j), dp + 6 * (i * np + j) + 3);
+    int nthr = pick_threads(n_threads);
+    #pragma omp parallel num_threads(nthr)
+    {
+        uint64_t* loc = calloc(nb, sizeof(uint64_t));
+        #pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < (int64_t)n; r++) {
+            if (!port_flag_g(&g, rec[r].pos, rec[r].status)) continue;
+            if (prec == ORC_F32) {
+                float L[3], v[3];
+                if (compat) {
+                    /* fluxAtObserverFast.C:1181 GetPoint() leaves the start at (0,0,0): line from the
+                     * origin through the exit point */
+                    const float* e = rec[r].pos;
+                    float inv = 1.0f / sqrtf(fmaf(e[0], e[0], fmaf(e[1], e[1], e[2] * e[2])));
+                    L[0] = L[1] = L[2] = 0.0f;
+                    v[0] = e[0] * inv; v[1] = e[1] * inv; v[2] = e[2] * inv;
+                } else {
+                    for (int c = 0; c < 3; c++) { L[c] = rec[r].pos[c]; v[c] = rec[r].dir[c]; }
+                }
+                for (int i = 0; i < nt; i++)
+                    for (int j = 0; j < np; j++)
+                        loc[i * np + j] += (uint64_t)line_hit_f32(&tab, i, j, L, v);
+            } else {
+                double L[3], v[3];
+                if (compat) {
+                    double e[3] = {rec[r].pos[0], rec[r].pos[1], rec[r].pos[2]};
+                    double mag = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                    L[0] = L[1] = L[2] = 0.0;
+                    v[0] = e[0] / mag; v[1] = e[1] / mag; v[2] = e[2] / mag;
+                } else {
+                    for (int c = 0; c < 3; c++) { L[c] = rec[r].pos[c]; v[c] = rec[r].dir[c]; }
+                }
+                for (int b = 0; b < nb; b++)
+                    loc[b] += (uint64_t)orc_detector_hit(dp + 6 * b, dp + 6 * b + 3, map->det_width, L, v);
+            }
+        }
+        #pragma omp critical
+        for (int b = 0; b < nb; b++) counts[b] += loc[b];
+        free(loc);
+    }
+    free(dp); free_tab_f(&tab);
+    return 0;
+}
+
+int orc_fluxmap(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                const orc_map_spec* map, int prec, uint64_t* counts, orc_stats* stats, int n_threads) {
+    const uint64_t chunk = 1u << 16;
+    orc_record* rec = malloc(sizeof(orc_record) * chunk);
+    orc_stats tot; memset(&tot, 0, sizeof tot);
+    int rc = 0;
+    for (uint64_t off = 0; off < n && !rc; off += chunk) {
+        uint64_t m = n - off < chunk ? n - off : chunk;
+        orc_stats s;
+        rc = orc_trace(sc, src, ray_id0 + off, m, seed, prec, rec, &s, n_threads);
+        if (!rc) rc = orc_map_records(sc, map, rec, m, prec, counts, n_threads);
+        tot.n_rays += s.n_rays; tot.n_exited += s.n_exited; tot.n_exit_port += s.n_exit_port;
+        tot.n_absorbed += s.n_absorbed; tot.n_suspended += s.n_suspended; tot.n_bounces += s.n_bounces;
+    }
+    free(rec);
+    if (stats) *stats = tot;
+    return rc;
+}
+
+/* ------------------------------------------------------------------ physical disks */
+void orc_sweep_pose(double theta, double phi, double r, double center[3], double rot[9]) {
+    /* integratingSphereDetectorSweep.C:150-171; TGeoRotation::RotateZ then RotateY act in the
+     * master frame: M = Ry(rotTheta) * Rz(rotPhi) */
+    double x = r * sin(theta * M_PI / 180.0) * cos(phi * M_PI / 180.0);
+    double y = r * sin(theta * M_PI / 180.0) * sin(phi * M_PI / 180.0);
+    double z = -r * cos(theta * M_PI / 180.0);
+    double dx = 0 - x, dy = 0 - y, dz = -100.0 - z;
+    double rotTheta = -atan2(sqrt(dx * dx + dy * dy), dz);
+    double rotPhi = atan2(dy, dx);
+    double cz = cos(rotPhi), sz = sin(rotPhi), cy = cos(rotTheta), sy = sin(rotTheta);
+    double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+    double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += Ry[3 * i + k] * Rz[3 * k + j];
+            rot[3 * i + j] = a;
+        }
+    center[0] = x; center[1] = y; center[2] = z;
+}
+
+/* segment (sphere crossing -> world-box point e) against a thin cylinder; IEEE ops only */
+static int disk_hit(const geom* g, const float* ef, const float* df, const double* c, const double* rot,
+                    double rad, double ht) {
+    double e[3] = {ef[0], ef[1], ef[2]}, d[3] = {df[0], df[1], df[2]};
+    double b = (e[0] * d[0] + e[1] * d[1]) + e[2] * d[2];
+    double cc = ((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]) - g->R1sq;
+    double disc = b * b - cc;
+    double smax = disc > 0.0 ? b - sqrt(disc) : b;
+    if (!(smax > 0.0)) return 0;
+    double a[3] = {rot[2], rot[5], rot[8]};
+    double rel[3] = {e[0] - c[0], e[1] - c[1], e[2] - c[2]};
+    double z0 = (rel[0] * a[0] + rel[1] * a[1]) + rel[2] * a[2];
+    double dz = -((d[0] * a[0] + d[1] * a[1]) + d[2] * a[2]);
+    double lo = 0.0, hi = smax;
+    if (dz != 0.0) {
+        double s0 = (-ht - z0) / dz, s1 = (ht - z0) / dz;
+        if (s0 > s1) { double t = s0; s0 = s1; s1 = t; }
+        if (s0 > lo) lo = s0;
+        if (s1 < hi) hi = s1;
+    } else if (fabs(z0) > ht) return 0;
+    if (lo > hi) return 0;
+    double rp[3], dp[3];
+    for (int i = 0; i < 3; i++) { rp[i] = rel[i] - z0 * a[i]; dp[i] = -d[i] - dz * a[i]; }
+    double qa = (dp[0] * dp[0] + dp[1] * dp[1]) + dp[2] * dp[2];
+    double qb = (rp[0] * dp[0] + rp[1] * dp[1]) + rp[2] * dp[2];
+    double qc = ((rp[0] * rp[0] + rp[1] * rp[1]) + rp[2] * rp[2]) - rad * rad;
+    if (qa > 0.0) {
+        double dd = qb * qb - qa * qc;
+        if (dd < 0.0) return 0;
+        double sq = sqrt(dd);
+        double s0 = (-qb - sq) / qa, s1 = (-qb + sq) / qa;
+        if (s0 > lo) lo = s0;
+        if (s1 < hi) hi = s1;
+    } else if (qc > 0.0) return 0;
+    return lo <= hi;
+}
+
+int orc_disk_hits(const orc_scene* sc, const orc_record* rec, uint64_t n, const double* det_center,
+                  const double* det_rot, uint32_t m, double det_r, double det_halfthick, uint64_t* hits) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    for (uint64_t r = 0; r < n; r++) {
+        if (rec[r].status != ORC_EXITED) continue;
+        for (uint32_t j = 0; j < m; j++)
+            hits[j] += (uint64_t)disk_hit(&g, rec[r].pos, rec[r].dir, det_center + 3 * j, det_rot + 9 * j, det_r, det_halfthick);
+    }
+    return 0;
+}

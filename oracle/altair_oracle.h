@@ -1,0 +1,148 @@
+/*
+ * altair_oracle.h -- CPU restatement of the reference's integrating-sphere hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (altair-raytracing_b200/,
+ * include/, macros) may include, link or call this.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
+ * and only as the checker / the CPU arm.
+ *
+ * PARITY STATUS: "parity unpinned" at the bit level.  The arithmetic of the path lives in
+ * ROOT 6.34.04 + ROBAST (un-vendored, not installable here), the
+ * reference has no tests and no dumped draws.  This oracle is pinned STATISTICALLY against
+ * the reference's committed outputs (tests/golden/, made by tests/golden/make_golden.py
+ * from /root/reference/flux_at_observer/ CSVs, 3dRayLog.txt, angular_dist.txt).
+ *
+ * Two arithmetic modes of the SAME algorithm:
+ *   prec = ORC_F64  straightforward double precision with libm sin/cos/log/sqrt -- the
+ *                   "physics" restatement that is checked against the reference goldens;
+ *   prec = ORC_F32  the documented single-precision operation sequence (DESIGN.md
+ *                   "arithmetic contract": IEEE add/mul/fma/div/sqrt only, polynomial
+ *                   sin/cos/log) that the CUDA kernels must reproduce bit for bit.
+ * Trajectories are chaotic (a 1-ulp change grows ~e-fold per few bounces), so per-ray
+ * replay equality is only meaningful against ORC_F32; ORC_F32 vs ORC_F64 is checked
+ * statistically and exactly on short chains (tests/test_oracle_modes.py).
+ *
+ * What it restates (reference file:line, all under /root/reference):
+ *   scene            flux_at_observer/fluxAtObserverFast.C:33-41,192-230
+ *                    makeIntegratingSphereNRays.C:25-39, integratingSphereDetectorSweep.C:114-123
+ *   source ray       flux_at_observer/fluxAtObserverFast.C:1147-1150
+ *   bounce loop      AOpticsManager::TraceNonSequential (ROBAST, call sites
+ *                    fluxAtObserverFast.C:1153, fluxAtObserverOptimize.C:295,
+ *                    makeIntegratingSphereNRays.C:67) -- algorithm per SURVEY.md appendix A
+ *   exit criterion   flux_at_observer/fluxAtObserverOptimize.C:309,323 (lastPoint z < -100)
+ *   detector         flux_at_observer/fluxAtObserverFast.C:61-80 (setPosition), :82-119
+ *                    (checkIntersection)
+ *   trace-once map   flux_at_observer/fluxAtObserverFast.C:1164-1303
+ *   BRDF mixture     flux_at_observer/nonLambertianFlux.C:147-208
+ *   direction hists  distributionSphereDetectorSweep.C:74-99
+ *   physical disk    integratingSphereDetectorSweep.C:134-172
+ */
+#ifndef ALTAIR_ORACLE_H
+#define ALTAIR_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same field order as altb_scene in include/altair_b200.h (declared independently). */
+typedef struct {
+    double r_inner, r_outer, theta_max_deg, world_half;
+    double reflectance, roughness_rad;
+    int32_t lambertian;   /* 1: diffuse model selected by brdf_kind; 0: ideal specular mirror */
+    int32_t max_bounces;  /* AOpticsManager::SetLimit */
+    int32_t brdf_kind;    /* 0 Lambert, 1 spec/diffuse mixture (nonLambertianFlux.C:147-208) */
+    int32_t count_all_status; /* 0: only EXITED rays can "pass the port" (batch macros read
+                                 GetExited/GetStopped only); 1: any status (single-ray macros) */
+    double brdf_param[4]; /* kind 1: roughness, specular, diffuse */
+    double exit_z;
+} orc_scene;
+
+typedef struct { double pos[3], dir[3]; } orc_source;
+
+typedef struct {
+    int32_t n_theta, n_phi;
+    double det_radius, det_width;
+    int32_t map_mode;      /* 0 LINE, 1 TRACEONCE_COMPAT, 2 DIRECTION */
+    int32_t pad_;
+} orc_map_spec;
+
+typedef struct {
+    uint64_t n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces;
+    double t_trace_s, t_map_s;
+} orc_stats;
+
+/* Per-ray result, identical layout to the kernels' 32-byte record. */
+typedef struct { float pos[3]; float dir[3]; uint32_t n_hits; uint32_t status; } orc_record;
+
+enum { ORC_EXITED = 1, ORC_ABSORBED = 2, ORC_SUSPENDED = 3, ORC_TAPE_END = 4 };
+enum { ORC_MAP_LINE = 0, ORC_MAP_TRACEONCE_COMPAT = 1, ORC_MAP_DIRECTION = 2 };
+enum { ORC_F64 = 0, ORC_F32 = 1 };
+
+#define ORC_DRAWS_PER_HIT 8
+/* draw record of one surface hit (f32):
+ *   [0] u_abs  [1] u_r  [2] u_phi  [3] u_sel      <- Philox block A  (counter word3 = 0)
+ *   [4] u_psi  [5] g0   [6] g1     [7] u_spare    <- Philox block B  (counter word3 = 1)
+ * u_* uniform on [0,1) with 24 bits; g0,g1 independent N(0,1) (Box-Muller of B.y,B.z). */
+
+/* Philox4x32-10 (Salmon et al. 2011), one block. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* The 8 f32 draws for (seed, ray_id, hit index k) exactly as the CUDA kernels derive them. */
+void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]);
+
+/* f32 math primitives of the arithmetic contract (exposed for unit tests). */
+void  orc_sincos2pi_f32(float u, float* s, float* c);
+void  orc_sincos_f32(float x, float* s, float* c);
+float orc_log_f32(float x);
+
+/* Trace rays ray_id0 .. ray_id0+n-1 with Philox draws; rec and/or stats may be NULL. */
+int orc_trace(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+              int prec, orc_record* rec, orc_stats* stats, int n_threads);
+/* Same, double outputs of the ORC_F64 state (for physics checks): pos[3n], dir[3n]. */
+int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                  double* pos, double* dir, uint32_t* n_hits, uint8_t* status, int n_threads);
+
+/* Replay: ray i starts at ray0[i] = (pos, dir) and consumes tape records
+ * tape[8*tape_off[i] .. 8*tape_off[i+1]).  Status ORC_TAPE_END if the tape runs out. */
+int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
+               uint64_t n, int prec, orc_record* rec);
+
+/* Generate the tape a Philox trace of the same rays would use (ORC_F32 trajectory).
+ * tape == NULL: only fills tape_off and returns the number of records needed.
+ * Returns number of records written; -3 when cap_records is too small. */
+int64_t orc_make_tape(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n,
+                      uint64_t seed, float* tape, uint64_t cap_records, uint64_t* tape_off);
+
+/* "Escaped through the port" flag of a record (fluxAtObserverOptimize.C:309,323). */
+int orc_port_flag(const orc_scene* sc, const orc_record* r);
+
+/* Map stage: counts[n_theta*n_phi] (theta-major) += contributions of the records.
+ * prec selects the arithmetic of the line-disk test (ORC_F64 = the reference's literal
+ * formula in double; ORC_F32 = the kernels' division-free f32 form).  Brute force. */
+int orc_map_records(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n,
+                    int prec, uint64_t* counts, int n_threads);
+int32_t orc_direction_bin(const orc_map_spec* map, const float d[3]);
+
+/* trace + map in one go (chunked; multi-threaded when n_threads != 1; <= 0 -> all cores). */
+int orc_fluxmap(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                const orc_map_spec* map, int prec, uint64_t* counts, orc_stats* stats, int n_threads);
+
+/* Detector pose / single test, literal double version of fluxAtObserverFast.C:61-119. */
+void orc_detector_pose(double theta_deg, double phi_deg, double radius, double pos[3], double nrm[3]);
+int  orc_detector_hit(const double pos[3], const double nrm[3], double width,
+                      const double line_pt[3], const double line_dir[3]);
+
+/* Physical thin-disk detectors (integratingSphereDetectorSweep.C:145-172): hits[j] += 1 when the
+ * escaping ray's last segment (sphere crossing -> world box) enters disk j. */
+int orc_disk_hits(const orc_scene* sc, const orc_record* rec, uint64_t n, const double* det_center,
+                  const double* det_rot, uint32_t m, double det_r, double det_halfthick, uint64_t* hits);
+void orc_sweep_pose(double theta_deg, double phi_deg, double r, double center[3], double rot[9]);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
