@@ -1,0 +1,690 @@
+// altb_api.cu -- C ABI (include/altair_b200.h) over the sm_100a kernels.  Host-side plumbing only:
+// scene validation, first-event setup, device buffers, launches, multi-device fan-out inside
+// one process.  No CPU fallback: every entry point needs a CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "altb_kernels.cuh"
+
+using namespace altb;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALTB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+static constexpr double PI_D = 3.14159265358979323846;
+static constexpr uint64_t DEFAULT_BATCH = 1ull << 26;
+
+struct DevCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    altb_record* rec = nullptr; uint64_t rec_cap = 0;
+    unsigned int* counter = nullptr;
+    unsigned long long* counts = nullptr; uint64_t counts_cap = 0;
+    unsigned long long* stats = nullptr;      // [8]
+    float* tables = nullptr; uint64_t tables_cap = 0;   // floats
+    float4* tiles = nullptr; uint64_t tiles_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct altb_ctx {
+    std::vector<DevCtx> devs;
+    uint64_t batch = DEFAULT_BATCH;
+    uint64_t launches = 0;
+};
+
+// ---------------------------------------------------------------------------------- scene setup
+static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
+    if (!(sc->r_inner > 0) || !(sc->r_outer >= sc->r_inner) || !(sc->world_half > sc->r_outer))
+        return fail(ALTB_E_SCENE, "scene: need 0 < r_inner <= r_outer < world_half");
+    if (!(sc->theta_max_deg > 90.0) || !(sc->theta_max_deg < 180.0))
+        return fail(ALTB_E_SCENE, "scene: theta_max_deg must be in (90,180)");
+    if (sc->max_bounces < 1) return fail(ALTB_E_SCENE, "scene: max_bounces < 1");
+    const double th = sc->theta_max_deg * PI_D / 180.0;
+    g.R1 = sc->r_inner; g.R2 = sc->r_outer;
+    g.R1sq = g.R1 * g.R1; g.R2sq = g.R2 * g.R2;
+    g.cth = cos(th); g.sth = sin(th);
+    g.zc = g.R1 * g.cth;
+    const double t = g.sth / g.cth;
+    g.T2 = t * t;
+    g.H = sc->world_half; g.exit_z = sc->exit_z;
+    g.lambertian = sc->lambertian; g.brdf_kind = sc->brdf_kind;
+    g.max_bounces = sc->max_bounces; g.count_all = sc->count_all_status;
+    double ps = 0.0, bs = 0.0;
+    if (sc->brdf_kind == 1) {
+        const double sum = sc->brdf_param[1] + sc->brdf_param[2];
+        if (!(sum > 0)) return fail(ALTB_E_SCENE, "scene: brdf specular+diffuse must be > 0");
+        ps = sc->brdf_param[1] / sum;
+        bs = sc->brdf_param[0] * PI_D / 6.0;
+    } else if (sc->brdf_kind != 0) return fail(ALTB_E_SCENE, "scene: brdf_kind %d not supported", sc->brdf_kind);
+    k.rho = (float)sc->reflectance; k.sigma = (float)sc->roughness_rad;
+    k.two_r1 = (float)(2.0 * g.R1); k.neg_inv_r1 = (float)(-1.0 / g.R1); k.nr_c = (float)(-0.5 / g.R1sq);
+    k.zc = (float)g.zc; k.p_spec = (float)ps; k.brdf_s = (float)bs; k.exit_zf = (float)g.exit_z;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- context
+extern "C" const char* altb_last_error(void) { return g_err.c_str(); }
+extern "C" int altb_version(void) { return ALTB_VERSION; }
+extern "C" int altb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void altb_destroy(altb_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        if (d.dev < 0) continue;
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles);
+        for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
+    if (!out) return fail(ALTB_E_ARG, "altb_create: out is NULL");
+    *out = nullptr;
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail < 1) {
+        cudaGetLastError();
+        return fail(ALTB_E_CUDA, "altb_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (n_devices <= 0) n_devices = devices ? 0 : avail;
+    if (n_devices < 1 || n_devices > avail) return fail(ALTB_E_ARG, "altb_create: n_devices=%d, visible=%d", n_devices, avail);
+    altb_ctx* ctx = new altb_ctx();
+    ctx->devs.resize(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        DevCtx& d = ctx->devs[i];
+        const int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= avail) { altb_destroy(ctx); return fail(ALTB_E_ARG, "altb_create: bad device %d", dev); }
+        cudaDeviceProp prop;
+        if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+            const char* msg = cudaGetErrorString(cudaGetLastError());
+            altb_destroy(ctx);
+            return fail(ALTB_E_CUDA, "altb_create: device %d init failed: %s", dev, msg);
+        }
+        d.dev = dev;
+        d.sm_count = prop.multiProcessorCount;
+        for (auto& ev : d.ev) cudaEventCreate(&ev);
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int altb_set_batch(altb_ctx* ctx, uint64_t batch_rays) {
+    if (!ctx) return fail(ALTB_E_ARG, "ctx is NULL");
+    ctx->batch = batch_rays ? batch_rays : DEFAULT_BATCH;
+    if (ctx->batch > (1ull << 31)) ctx->batch = 1ull << 31;
+    return 0;
+}
+
+extern "C" uint64_t altb_launch_count(const altb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+template <typename T>
+static int ensure(T*& p, uint64_t& cap, uint64_t need) {
+    if (need <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    CK(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- trace launch
+struct TraceSetup { TraceParams P; bool rough; int model; };
+
+static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t seed, TraceSetup& ts) {
+    if (int rc = make_geom(sc, ts.P.g, ts.P.k)) return rc;
+    const int kind0 = launch_ray(ts.P.g, src->pos, src->dir, ts.P.d0, ts.P.x0);
+    if (kind0 < 0) return fail(ALTB_E_SOURCE, "source must lie strictly inside the inner sphere with a non-zero direction");
+    ts.P.kind0 = kind0;
+    ts.P.seed = seed;
+    ts.rough = sc->roughness_rad != 0.0;
+    ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : 0);
+    return 0;
+}
+
+template <bool R, int M>
+static void launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
+    k_trace<R, M><<<blocks, 256, 0, st>>>(P, rec, counter);
+}
+
+static int trace_blocks_per_sm(bool rough, int model) {
+    int b = 0;
+#define OCC(R, M) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<R, M>, 256, 0)
+    if (rough) { if (model == 0) OCC(true, 0); else if (model == 1) OCC(true, 1); else OCC(true, 2); }
+    else       { if (model == 0) OCC(false, 0); else if (model == 1) OCC(false, 1); else OCC(false, 2); }
+#undef OCC
+    return b > 0 ? b : 1;
+}
+
+// trace rays [ray_id0, ray_id0+n) into d.rec[0..n)
+static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, uint64_t ray_id0, uint32_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (ts.P.kind0 == EV_EXIT) {   // the source points straight out of the port: every ray is the same record
+        altb_record proto;
+        for (int i = 0; i < 3; i++) { proto.pos[i] = (float)ts.P.x0[i]; proto.dir[i] = (float)ts.P.d0[i]; }
+        proto.n_hits = 0; proto.status = ALTB_EXITED;
+        k_fill_records<<<d.sm_count * 4, 256, 0, st>>>(d.rec, n, proto);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    TraceParams& P = ts.P;
+    P.ray_id0 = ray_id0; P.n = n;
+    const int per_sm = trace_blocks_per_sm(ts.rough, ts.model);
+    int blocks = d.sm_count * per_sm;
+    const uint32_t warps_needed = (n + 31) / 32;
+    if ((uint32_t)blocks * 8u > warps_needed) blocks = (int)((warps_needed + 7) / 8);
+    // ids are claimed in chunks; small enough that the tail (last chunk per warp) stays short
+    uint32_t chunk = 256;
+    while (chunk > 32 && (uint64_t)chunk * blocks * 8 * 4 > n) chunk >>= 1;
+    P.chunk = chunk;
+    CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
+    if (ts.rough) {
+        if (ts.model == 0) launch_trace_t<true, 0>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 1) launch_trace_t<true, 1>(P, d.rec, d.counter, blocks, st);
+        else launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
+    } else {
+        if (ts.model == 0) launch_trace_t<false, 0>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 1) launch_trace_t<false, 1>(P, d.rec, d.counter, blocks, st);
+        else launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- map setup
+struct MapSetup { MapParams M; int n_tiles; size_t line_smem; size_t dir_smem; };
+
+static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KConsts& k, const altb_map_spec* map,
+                     MapSetup& ms, cudaStream_t st) {
+    (void)sc;
+    if (map->n_theta < 1 || map->n_phi < 1 || (int64_t)map->n_theta * map->n_phi > (1 << 24))
+        return fail(ALTB_E_ARG, "map: bad bin counts %d x %d", map->n_theta, map->n_phi);
+    if (map->map_mode < ALTB_MAP_LINE || map->map_mode > ALTB_MAP_DIRECTION) return fail(ALTB_E_ARG, "map: bad map_mode %d", map->map_mode);
+    MapParams& M = ms.M;
+    memset(&M, 0, sizeof M);
+    const int nt = map->n_theta, np = map->n_phi;
+    M.n_theta = nt; M.n_phi = np; M.mode = map->map_mode;
+    M.count_all = g.count_all; M.exit_zf = k.exit_zf;
+    const double hw = map->det_width / 2;
+    M.w2 = (float)(hw * hw);
+    ms.dir_smem = (size_t)nt * np * sizeof(unsigned int);
+    M.use_smem_hist = ms.dir_smem <= 160 * 1024;
+    if (!M.use_smem_hist) ms.dir_smem = 0;
+    ms.n_tiles = 0; ms.line_smem = 0;
+    if (map->map_mode == ALTB_MAP_DIRECTION) return 0;
+    if (!(map->det_radius > 0) || !(map->det_width > 0)) return fail(ALTB_E_ARG, "map: det_radius/det_width must be > 0");
+
+    // per-row / per-column tables (Detector::setPosition, fluxAtObserverFast.C:61-80), rounded once to f32
+    std::vector<float> tab((size_t)4 * nt + 2 * np);
+    std::vector<double> px((size_t)nt * np), py((size_t)nt * np), pzv((size_t)nt * np);
+    for (int i = 0; i < nt; i++) {
+        const double th = (i + 0.5) * 90.0 / nt * PI_D / 180.0;
+        tab[i] = (float)(map->det_radius * sin(th));            // rs
+        tab[nt + i] = (float)(-100.0 - map->det_radius * cos(th));  // pz
+        tab[2 * nt + i] = (float)sin(th);                       // st
+        tab[3 * nt + i] = (float)cos(th);                       // ct
+    }
+    for (int j = 0; j < np; j++) {
+        const double ph = (j + 0.5) * 360.0 / np * PI_D / 180.0;
+        tab[4 * nt + j] = (float)cos(ph);
+        tab[4 * nt + np + j] = (float)sin(ph);
+    }
+    for (int i = 0; i < nt; i++)
+        for (int j = 0; j < np; j++) {
+            px[(size_t)i * np + j] = (double)tab[i] * tab[4 * nt + j];
+            py[(size_t)i * np + j] = (double)tab[i] * tab[4 * nt + np + j];
+            pzv[(size_t)i * np + j] = tab[nt + i];
+        }
+    // tile shape: the (t_theta x t_phi) <= 32 bins with the smallest mean bounding radius
+    const int shapes[6][2] = {{32, 1}, {16, 2}, {8, 4}, {4, 8}, {2, 16}, {1, 32}};
+    double best = 1e300; int bt = 8, bp = 4;
+    std::vector<float4> best_tiles;
+    for (auto& s : shapes) {
+        const int tt = s[0], tp = s[1];
+        const int ntt = (nt + tt - 1) / tt, ntp = (np + tp - 1) / tp;
+        if ((size_t)ntt * ntp > 4096) continue;
+        std::vector<float4> tl((size_t)ntt * ntp);
+        double sum = 0;
+        for (int a = 0; a < ntt; a++)
+            for (int b = 0; b < ntp; b++) {
+                double cx = 0, cy = 0, cz = 0; int cnt = 0;
+                for (int i = a * tt; i < std::min(nt, (a + 1) * tt); i++)
+                    for (int j = b * tp; j < std::min(np, (b + 1) * tp); j++) {
+                        cx += px[(size_t)i * np + j]; cy += py[(size_t)i * np + j]; cz += pzv[(size_t)i * np + j]; cnt++;
+                    }
+                cx /= cnt; cy /= cnt; cz /= cnt;
+                double r = 0;
+                for (int i = a * tt; i < std::min(nt, (a + 1) * tt); i++)
+                    for (int j = b * tp; j < std::min(np, (b + 1) * tp); j++) {
+                        const double dx = px[(size_t)i * np + j] - cx, dy = py[(size_t)i * np + j] - cy, dz = pzv[(size_t)i * np + j] - cz;
+                        r = std::max(r, sqrt(dx * dx + dy * dy + dz * dz));
+                    }
+                sum += r;
+                const double rad = hw + r + 0.5;     // conservative: disk radius + tile radius + f32 slack [cm]
+                tl[(size_t)a * ntp + b] = make_float4((float)cx, (float)cy, (float)cz, (float)(rad * rad * 1.0001));
+            }
+        const double mean = sum / ((double)ntt * ntp) + 1e-9 * ntt * ntp;   // tie-break: fewer tiles
+        if (mean < best) { best = mean; bt = tt; bp = tp; best_tiles.swap(tl); }
+    }
+    M.t_theta = bt; M.t_phi = bp;
+    M.nt_theta = (nt + bt - 1) / bt; M.nt_phi = (np + bp - 1) / bp;
+    ms.n_tiles = M.nt_theta * M.nt_phi;
+    ms.line_smem = (size_t)LINE_BATCH * 6 * sizeof(float) + (size_t)ms.n_tiles * LINE_WORDS * sizeof(uint32_t) +
+                   ((size_t)4 * nt + 2 * np) * sizeof(float);
+    if (ms.line_smem > 200 * 1024) return fail(ALTB_E_ARG, "map: %d x %d bins need %zu B of shared memory", nt, np, ms.line_smem);
+    if (int rc = ensure(d.tables, d.tables_cap, (uint64_t)tab.size())) return rc;
+    if (int rc = ensure(d.tiles, d.tiles_cap, (uint64_t)best_tiles.size())) return rc;
+    CK(cudaMemcpyAsync(d.tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d.tiles, best_tiles.data(), best_tiles.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // the host vectors die at return
+    M.rs = d.tables; M.pz = d.tables + nt; M.st = d.tables + 2 * nt; M.ct = d.tables + 3 * nt;
+    M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
+    M.tiles = d.tiles;
+    return 0;
+}
+
+// records d.rec[0..n) -> counts (+stats)
+static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, unsigned long long* d_counts,
+                   unsigned long long* d_stats, int* d_bin, cudaStream_t st) {
+    if (n == 0) return 0;
+    const MapParams& M = ms.M;
+    if (M.mode == ALTB_MAP_DIRECTION) {
+        static bool attr_done = false;
+        if (ms.dir_smem > 48 * 1024 && !attr_done) {
+            CK(cudaFuncSetAttribute(k_map_direction, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_done = true;
+        }
+        int blocks = d.sm_count * 2;
+        const int need = (int)((n + 255) / 256);
+        if (blocks > need) blocks = need;
+        k_map_direction<<<blocks, 256, ms.dir_smem, st>>>(d.rec, n, M, d_counts, d_stats, d_bin);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    if (d_stats) {
+        int blocks = d.sm_count * 4;
+        const int need = (int)((n + 255) / 256);
+        if (blocks > need) blocks = need;
+        k_stats<<<blocks, 256, 0, st>>>(d.rec, n, M.count_all, M.exit_zf, d_stats);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    static bool attr_line = false;
+    if (!attr_line) {
+        CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_line = true;
+    }
+    int per_sm = (int)((220 * 1024) / (ms.line_smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int blocks = d.sm_count * per_sm;
+    const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
+    if (blocks > need) blocks = need;
+    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.rec, n, M, d_counts);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- hot path
+static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes, int n_scenes, const altb_source* src,
+                             uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
+                             unsigned long long* d_counts, unsigned long long* d_stats, cudaStream_t st,
+                             float* t_trace_ms, float* t_map_ms) {
+    CK(cudaSetDevice(d.dev));
+    const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
+    const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n_rays, 1));
+    if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
+    for (int s = 0; s < n_scenes; s++) {
+        TraceSetup ts;
+        if (int rc = setup_trace(&scenes[s], src, seed, ts)) return rc;
+        MapSetup ms;
+        if (int rc = setup_map(d, &scenes[s], ts.P.g, ts.P.k, map, ms, st)) return rc;
+        float tt = 0.f, tm = 0.f;
+        for (uint64_t off = 0; off < n_rays; off += batch) {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
+            if (t_trace_ms) CK(cudaEventRecord(d.ev[0], st));
+            if (int rc = run_trace(ctx, d, ts, ray_id0 + off, n, st)) return rc;
+            if (t_trace_ms) CK(cudaEventRecord(d.ev[1], st));
+            if (int rc = run_map(ctx, d, ms, n, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, st)) return rc;
+            if (t_trace_ms) {
+                CK(cudaEventRecord(d.ev[2], st));
+                CK(cudaEventSynchronize(d.ev[2]));
+                float a = 0.f, b = 0.f;
+                CK(cudaEventElapsedTime(&a, d.ev[0], d.ev[1]));
+                CK(cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
+                tt += a; tm += b;
+            }
+        }
+        if (t_trace_ms) { t_trace_ms[s] = tt; t_map_ms[s] = tm; }
+    }
+    return 0;
+}
+
+extern "C" int altb_trace_fluxmap_dev(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
+                                      uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
+                                      uint64_t* d_counts, uint64_t* d_stats, void* cuda_stream) {
+    if (!ctx || !scenes || n_scenes < 1 || !src || !map || !d_counts) return fail(ALTB_E_ARG, "altb_trace_fluxmap_dev: NULL/empty argument");
+    return fluxmap_on_device(ctx, ctx->devs[0], scenes, n_scenes, src, ray_id0, n_rays, seed, map,
+                             reinterpret_cast<unsigned long long*>(d_counts), reinterpret_cast<unsigned long long*>(d_stats),
+                             (cudaStream_t)cuda_stream, nullptr, nullptr);
+}
+
+extern "C" int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
+                                  uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
+                                  uint64_t* counts, altb_stats* stats) {
+    if (!ctx || !scenes || n_scenes < 1 || !src || !map || !counts) return fail(ALTB_E_ARG, "altb_trace_fluxmap: NULL/empty argument");
+    const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
+    const int nd = (int)ctx->devs.size();
+    const uint64_t words = (uint64_t)n_scenes * (nb + 8);
+    // rays are split evenly over the context's devices; each accumulates its own map, the host adds them
+    std::vector<std::vector<float>> tms(nd, std::vector<float>(2 * n_scenes, 0.f));
+    for (int i = 0; i < nd; i++) {
+        DevCtx& d = ctx->devs[i];
+        CK(cudaSetDevice(d.dev));
+        if (int rc = ensure(d.counts, d.counts_cap, words)) return rc;
+        CK(cudaMemsetAsync(d.counts, 0, words * sizeof(unsigned long long), d.stream));
+    }
+    // launch everything first when more than one device is used (async), time per device when one
+    for (int i = 0; i < nd; i++) {
+        DevCtx& d = ctx->devs[i];
+        const uint64_t lo = n_rays * i / nd, hi = n_rays * (i + 1) / nd;
+        float* tt = nd == 1 ? tms[i].data() : nullptr;
+        float* tm = nd == 1 ? tms[i].data() + n_scenes : nullptr;
+        if (int rc = fluxmap_on_device(ctx, d, scenes, n_scenes, src, ray_id0 + lo, hi - lo, seed, map,
+                                       d.counts, d.counts + (size_t)n_scenes * nb, d.stream, tt, tm)) return rc;
+    }
+    std::vector<unsigned long long> host(words);
+    if (stats) memset(stats, 0, sizeof(altb_stats) * n_scenes);
+    for (int i = 0; i < nd; i++) {
+        DevCtx& d = ctx->devs[i];
+        CK(cudaSetDevice(d.dev));
+        CK(cudaMemcpyAsync(host.data(), d.counts, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        for (uint64_t j = 0; j < (uint64_t)n_scenes * nb; j++) counts[j] += host[j];
+        if (stats)
+            for (int s = 0; s < n_scenes; s++) {
+                const unsigned long long* p = host.data() + (size_t)n_scenes * nb + (size_t)s * 8;
+                stats[s].n_rays += p[0]; stats[s].n_exited += p[1]; stats[s].n_exit_port += p[2];
+                stats[s].n_absorbed += p[3]; stats[s].n_suspended += p[4]; stats[s].n_bounces += p[5];
+                stats[s].t_trace_s += tms[i][s] * 1e-3; stats[s].t_map_s += tms[i][n_scenes + s] * 1e-3;
+            }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- per-ray results
+static void read_stats(const unsigned long long* p, altb_stats* s) {
+    memset(s, 0, sizeof *s);
+    s->n_rays = p[0]; s->n_exited = p[1]; s->n_exit_port = p[2]; s->n_absorbed = p[3]; s->n_suspended = p[4]; s->n_bounces = p[5];
+}
+
+extern "C" int altb_trace_records(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                                  uint64_t n_rays, uint64_t seed, altb_record* records, altb_stats* stats) {
+    if (!ctx || !scene || !src || (!records && n_rays)) return fail(ALTB_E_ARG, "altb_trace_records: NULL argument");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    TraceSetup ts;
+    if (int rc = setup_trace(scene, src, seed, ts)) return rc;
+    const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n_rays, 1));
+    if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
+    CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    for (uint64_t off = 0; off < n_rays; off += batch) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
+        if (int rc = run_trace(ctx, d, ts, ray_id0 + off, n, d.stream)) return rc;
+        if (stats) {
+            k_stats<<<d.sm_count * 4, 256, 0, d.stream>>>(d.rec, n, ts.P.g.count_all, ts.P.k.exit_zf, d.stats);
+            ctx->launches++;
+        }
+        CK(cudaMemcpyAsync(records + off, d.rec, (size_t)n * sizeof(altb_record), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    CK(cudaEventSynchronize(d.ev[1]));
+    if (stats) {
+        unsigned long long h[8];
+        CK(cudaMemcpy(h, d.stats, sizeof h, cudaMemcpyDeviceToHost));
+        read_stats(h, stats);
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+        stats->t_trace_s = ms * 1e-3;
+    }
+    return 0;
+}
+
+extern "C" int altb_trace_exit_rays(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                                    uint64_t n_rays, uint64_t seed, double* last_pos, double* last_dir,
+                                    uint32_t* n_points, uint8_t* status, altb_stats* stats) {
+    if (!ctx || !scene || !src) return fail(ALTB_E_ARG, "altb_trace_exit_rays: NULL argument");
+    const uint64_t step = 1ull << 22;
+    std::vector<altb_record> buf((size_t)std::min<uint64_t>(step, std::max<uint64_t>(n_rays, 1)));
+    altb_stats tot; memset(&tot, 0, sizeof tot);
+    for (uint64_t off = 0; off < n_rays; off += step) {
+        const uint64_t n = std::min<uint64_t>(step, n_rays - off);
+        altb_stats s;
+        if (int rc = altb_trace_records(ctx, scene, src, ray_id0 + off, n, seed, buf.data(), &s)) return rc;
+        for (uint64_t i = 0; i < n; i++) {
+            const altb_record& r = buf[i];
+            for (int c = 0; c < 3; c++) {
+                if (last_pos) last_pos[3 * (off + i) + c] = r.pos[c];
+                if (last_dir) last_dir[3 * (off + i) + c] = r.dir[c];
+            }
+            if (n_points) n_points[off + i] = 1 + r.n_hits + (r.status == ALTB_EXITED ? 1u : 0u);
+            if (status) status[off + i] = (uint8_t)r.status;
+        }
+        tot.n_rays += s.n_rays; tot.n_exited += s.n_exited; tot.n_exit_port += s.n_exit_port; tot.n_absorbed += s.n_absorbed;
+        tot.n_suspended += s.n_suspended; tot.n_bounces += s.n_bounces; tot.t_trace_s += s.t_trace_s;
+    }
+    if (stats) *stats = tot;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- map on host records
+extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
+                                const altb_record* records, uint64_t n, uint64_t* counts) {
+    if (!ctx || !scene || !map || (!records && n) || !counts) return fail(ALTB_E_ARG, "altb_map_records: NULL argument");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    Geom g; KConsts k;
+    if (int rc = make_geom(scene, g, k)) return rc;
+    MapSetup ms;
+    if (int rc = setup_map(d, scene, g, k, map, ms, d.stream)) return rc;
+    const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
+    if (int rc = ensure(d.counts, d.counts_cap, nb + 8)) return rc;
+    CK(cudaMemsetAsync(d.counts, 0, nb * sizeof(unsigned long long), d.stream));
+    const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n, 1));
+    if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
+    for (uint64_t off = 0; off < n; off += batch) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(batch, n - off);
+        CK(cudaMemcpyAsync(d.rec, records + off, (size_t)m * sizeof(altb_record), cudaMemcpyHostToDevice, d.stream));
+        if (int rc = run_map(ctx, d, ms, m, d.counts, nullptr, nullptr, d.stream)) return rc;
+    }
+    std::vector<unsigned long long> host(nb);
+    CK(cudaMemcpyAsync(host.data(), d.counts, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    for (uint64_t j = 0; j < nb; j++) counts[j] += host[j];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- physical disks
+extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                                   uint64_t n_rays, uint64_t seed, const double* det_center, const double* det_rot,
+                                   uint32_t m, double det_r, double det_halfthick, uint64_t* hits, altb_stats* stats) {
+    if (!ctx || !scene || !src || !det_center || !det_rot || !hits || m == 0) return fail(ALTB_E_ARG, "altb_detector_sweep: NULL/empty argument");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    TraceSetup ts;
+    if (int rc = setup_trace(scene, src, seed, ts)) return rc;
+    const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n_rays, 1));
+    if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
+    double* d_geo = nullptr;
+    unsigned long long* d_hits = nullptr;
+    CK(cudaMalloc(&d_geo, (size_t)m * 12 * sizeof(double)));
+    if (cudaMalloc(&d_hits, (size_t)m * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(d_geo); return fail(ALTB_E_NOMEM, "cudaMalloc hits"); }
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(d_geo, det_center, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_geo + (size_t)m * 3, det_rot, (size_t)m * 9 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess ||
+            cudaMemsetAsync(d_hits, 0, (size_t)m * sizeof(unsigned long long), d.stream) != cudaSuccess ||
+            cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "detector_sweep: upload failed"); break; }
+        for (uint64_t off = 0; off < n_rays && !rc; off += batch) {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
+            rc = run_trace(ctx, d, ts, ray_id0 + off, n, d.stream);
+            if (rc) break;
+            k_stats<<<d.sm_count * 4, 256, 0, d.stream>>>(d.rec, n, ts.P.g.count_all, ts.P.k.exit_zf, d.stats);
+            int blocks = d.sm_count * 4;
+            const int need = (int)((n + 7) / 8);
+            if (blocks > need) blocks = need;
+            k_disk_hits<<<blocks, 256, 0, d.stream>>>(d.rec, n, ts.P.g, d_geo, d_geo + (size_t)m * 3, m, det_r, det_halfthick, d_hits);
+            ctx->launches += 2;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ALTB_E_CUDA, "detector_sweep: launch failed");
+        }
+        if (rc) break;
+        std::vector<unsigned long long> h(m);
+        unsigned long long hs[8];
+        if (cudaMemcpyAsync(h.data(), d_hits, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream) != cudaSuccess ||
+            cudaMemcpyAsync(hs, d.stats, sizeof hs, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess ||
+            cudaStreamSynchronize(d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "detector_sweep: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        for (uint32_t j = 0; j < m; j++) hits[j] += h[j];
+        if (stats) read_stats(hs, stats);
+    } while (0);
+    cudaFree(d_geo); cudaFree(d_hits);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- replay
+template <bool R, int M>
+static void launch_replay_t(const ReplayParams& P, const double* ray0, const float4* tape, const unsigned long long* off,
+                            altb_record* rec, cudaStream_t st) {
+    k_replay<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, rec);
+}
+
+extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
+                           const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map,
+                           altb_record* records, int32_t* bin, uint8_t* port) {
+    if (!ctx || !scene || !ray0 || !tape_off || (!tape && n_rays && tape_off[n_rays])) return fail(ALTB_E_ARG, "altb_replay: NULL argument");
+    if (n_rays == 0) return 0;
+    if (n_rays > (1ull << 31)) return fail(ALTB_E_ARG, "altb_replay: at most 2^31 rays per call");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    ReplayParams P;
+    if (int rc = make_geom(scene, P.g, P.k)) return rc;
+    P.n = (uint32_t)n_rays;
+    const bool rough = scene->roughness_rad != 0.0;
+    const int model = !scene->lambertian ? 2 : (scene->brdf_kind == 1 ? 1 : 0);
+    const uint64_t n_rec = tape_off[n_rays];
+    if (int rc = ensure(d.rec, d.rec_cap, n_rays)) return rc;
+    double* d_ray0 = nullptr; float* d_tape = nullptr; unsigned long long* d_off = nullptr; int* d_bin = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&d_ray0, n_rays * 6 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&d_tape, std::max<uint64_t>(n_rec, 1) * 8 * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&d_off, (n_rays + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d_bin, n_rays * sizeof(int)) != cudaSuccess) { rc = fail(ALTB_E_NOMEM, "altb_replay: cudaMalloc failed"); break; }
+        if (cudaMemcpyAsync(d_ray0, ray0, n_rays * 6 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess ||
+            (n_rec && cudaMemcpyAsync(d_tape, tape, n_rec * 8 * sizeof(float), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) ||
+            cudaMemcpyAsync(d_off, tape_off, (n_rays + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) {
+            rc = fail(ALTB_E_CUDA, "altb_replay: upload failed"); break;
+        }
+        const float4* t4 = reinterpret_cast<const float4*>(d_tape);
+        if (rough) {
+            if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+        } else {
+            if (model == 0) launch_replay_t<false, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else if (model == 1) launch_replay_t<false, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+        }
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: launch failed"); break; }
+        std::vector<altb_record> tmp;
+        altb_record* out = records;
+        if (!out) { tmp.resize(n_rays); out = tmp.data(); }
+        if (bin && map) {
+            MapSetup ms;
+            altb_map_spec m2 = *map; m2.map_mode = ALTB_MAP_DIRECTION;
+            rc = setup_map(d, scene, P.g, P.k, &m2, ms, d.stream);
+            if (rc) break;
+            MapParams M = ms.M; M.use_smem_hist = 0;
+            k_map_direction<<<d.sm_count * 2, 256, 0, d.stream>>>(d.rec, (uint32_t)n_rays, M, nullptr, nullptr, d_bin);
+            ctx->launches++;
+            if (cudaMemcpyAsync(bin, d_bin, n_rays * sizeof(int), cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: download failed"); break; }
+        }
+        if (cudaMemcpyAsync(out, d.rec, n_rays * sizeof(altb_record), cudaMemcpyDeviceToHost, d.stream) != cudaSuccess ||
+            cudaStreamSynchronize(d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (port)
+            for (uint64_t i = 0; i < n_rays; i++)
+                port[i] = (uint8_t)((P.g.count_all || out[i].status == ALTB_EXITED) && out[i].pos[2] < P.k.exit_zf);
+    } while (0);
+    cudaFree(d_ray0); cudaFree(d_tape); cudaFree(d_off); cudaFree(d_bin);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- RNG probe
+extern "C" int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, float* out) {
+    if (!ctx || (!out && n)) return fail(ALTB_E_ARG, "altb_draws: NULL argument");
+    if (n == 0) return 0;
+    if (n > (1ull << 28)) return fail(ALTB_E_ARG, "altb_draws: n too large");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    float* buf = nullptr;
+    CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
+    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(seed, ray_id0, (uint32_t)n, k, buf);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, buf, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(ALTB_E_CUDA, "altb_draws: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- FP32 peak probe
+extern "C" int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(ALTB_E_ARG, "altb_measure_fp32_peak: NULL argument");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    float* buf = nullptr;
+    CK(cudaMalloc(&buf, 16));
+    const int iters = 4096, blocks = d.sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        k_fma_peak<<<blocks, 256, 0, d.stream>>>(buf, iters);
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        CK(cudaEventSynchronize(d.ev[1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+        const double flop = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0) best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+        ctx->launches++;
+    }
+    cudaFree(buf);
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,137 @@
+// altb_geom.cuh -- scene constants and the double-precision "slow path" (port crossing, conical
+// port edge between r_inner and r_outer, world box), shared by host setup code and the kernels.
+// Only IEEE + - * / sqrt, no contraction (-fmad=false / -ffp-contract=off).
+// Geometry follows SURVEY.md appendix A.1-A.3 (TGeoSphere(rmin,rmax,0,thetaMax) + TGeoBBox world of
+// flux_at_observer/fluxAtObserverFast.C:199-204).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define ALTB_HD __host__ __device__ __forceinline__
+
+namespace altb {
+
+enum { EV_WALL = 1, EV_EDGE = 2, EV_EXIT = 3 };
+
+struct Geom {
+    double R1, R2, R1sq, R2sq, zc, T2, cth, sth, H, exit_z;
+    int lambertian, brdf_kind, max_bounces, count_all;
+};
+
+struct KConsts { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf; };
+
+struct TraceParams {
+    Geom g;
+    KConsts k;
+    int kind0;            // first event of the (identical) source rays
+    double x0[3];         // its point
+    double d0[3];         // unit source direction
+    uint64_t seed;
+    uint64_t ray_id0;     // global id of local ray 0
+    uint32_t n;           // rays in this launch
+    uint32_t chunk;       // ids a warp claims at a time
+};
+
+ALTB_HD void box_exit(const Geom& g, const double* x, const double* d, double* e) {
+    double t = INFINITY;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double ti;
+        if (d[i] > 0.0) ti = (g.H - x[i]) / d[i];
+        else if (d[i] < 0.0) ti = (-g.H - x[i]) / d[i];
+        else continue;
+        if (ti < t) t = ti;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) e[i] = x[i] + t * d[i];
+}
+
+// x0 = inner-sphere crossing inside the opening, heading outward: EDGE(q) or EXIT(e)
+ALTB_HD int cap_crossing(const Geom& g, const double* x0, const double* d, double* out) {
+    double A = (d[0] * d[0] + d[1] * d[1]) - g.T2 * (d[2] * d[2]);
+    double B = (x0[0] * d[0] + x0[1] * d[1]) - g.T2 * (x0[2] * d[2]);
+    double C = (x0[0] * x0[0] + x0[1] * x0[1]) - g.T2 * (x0[2] * x0[2]);
+    double disc = B * B - A * C;
+    double s = 0.0;
+    bool have = false;
+    if (disc >= 0.0) {
+        double sq = sqrt(disc);
+        if (B > 0.0) { double den = B + sq; if (den > 0.0) { s = -C / den; have = true; } }
+        else if (A > 0.0) { s = (sq - B) / A; have = true; }
+    }
+    if (have && s > 0.0) {
+        double q0 = x0[0] + s * d[0], q1 = x0[1] + s * d[1], q2 = x0[2] + s * d[2];
+        if (q2 < 0.0) {
+            double r2 = (q0 * q0 + q1 * q1) + q2 * q2;
+            if (r2 <= g.R2sq) { out[0] = q0; out[1] = q1; out[2] = q2; return EV_EDGE; }
+        }
+    }
+    box_exit(g, x0, d, out);
+    return EV_EXIT;
+}
+
+// q on the conical port edge, d heading into the opening: WALL / EDGE / EXIT
+ALTB_HD int from_edge(const Geom& g, const double* q, const double* d, double* out) {
+    double A = (d[0] * d[0] + d[1] * d[1]) - g.T2 * (d[2] * d[2]);
+    double B = (q[0] * d[0] + q[1] * d[1]) - g.T2 * (q[2] * d[2]);
+    double s_c = INFINITY, xc0 = 0.0, xc1 = 0.0, xc2 = 0.0;
+    if (A > 0.0 && B < 0.0) {
+        double s = (-2.0 * B) / A;
+        double x0 = q[0] + s * d[0], x1 = q[1] + s * d[1], x2 = q[2] + s * d[2];
+        if (x2 < 0.0) {
+            double r2 = (x0 * x0 + x1 * x1) + x2 * x2;
+            if (r2 >= g.R1sq && r2 <= g.R2sq) { s_c = s; xc0 = x0; xc1 = x1; xc2 = x2; }
+        }
+    }
+    double s_in = INFINITY;
+    double b = (q[0] * d[0] + q[1] * d[1]) + q[2] * d[2];
+    double c0 = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) - g.R1sq;
+    if (b < 0.0) {
+        if (c0 > 0.0) { double disc = b * b - c0; if (disc > 0.0) s_in = -b - sqrt(disc); }
+        else s_in = 0.0;
+    }
+    if (s_c < s_in) { out[0] = xc0; out[1] = xc1; out[2] = xc2; return EV_EDGE; }
+    if (s_in < INFINITY) {
+        double xin[3] = {q[0] + s_in * d[0], q[1] + s_in * d[1], q[2] + s_in * d[2]};
+        double bb = (xin[0] * d[0] + xin[1] * d[1]) + xin[2] * d[2];
+        double cc = ((xin[0] * xin[0] + xin[1] * xin[1]) + xin[2] * xin[2]) - g.R1sq;
+        double disc = bb * bb - cc;
+        if (disc < 0.0) disc = 0.0;
+        double t = sqrt(disc) - bb;
+        double h[3] = {xin[0] + t * d[0], xin[1] + t * d[1], xin[2] + t * d[2]};
+        double sc = g.R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+        h[0] *= sc; h[1] *= sc; h[2] *= sc;
+        if (h[2] >= g.zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+        return cap_crossing(g, h, d, out);
+    }
+    box_exit(g, q, d, out);
+    return EV_EXIT;
+}
+
+// normal of the conical edge at q, pointing into the opening (theta-hat at theta_max)
+ALTB_HD void edge_normal(const Geom& g, const double* q, double* n) {
+    double rho = sqrt(q[0] * q[0] + q[1] * q[1]);
+    if (rho > 0.0) { n[0] = g.cth * (q[0] / rho); n[1] = g.cth * (q[1] / rho); }
+    else { n[0] = 0.0; n[1] = 0.0; }
+    n[2] = -g.sth;
+}
+
+// first event of a ray launched at p0 (inside the cavity) along dir (appendix A.2); <0 on error
+ALTB_HD int launch_ray(const Geom& g, const double* p0, const double* dir, double* d0, double* out) {
+    double m = sqrt((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+    if (!(m > 0.0)) return -1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) d0[i] = dir[i] / m;
+    double b = (p0[0] * d0[0] + p0[1] * d0[1]) + p0[2] * d0[2];
+    double c0 = ((p0[0] * p0[0] + p0[1] * p0[1]) + p0[2] * p0[2]) - g.R1sq;
+    if (!(c0 < 0.0)) return -1;
+    double t = sqrt(b * b - c0) - b;
+    double h[3] = {p0[0] + t * d0[0], p0[1] + t * d0[1], p0[2] + t * d0[2]};
+    double sc = g.R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+    h[0] *= sc; h[1] *= sc; h[2] *= sc;
+    if (h[2] >= g.zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+    return cap_crossing(g, h, d0, out);
+}
+
+}  // namespace altb

@@ -1,0 +1,144 @@
+/*
+ * altair_b200.h -- C ABI of the B200-native integrating-sphere photon tracer.
+ *
+ * This is the drop-in boundary for ONE hot path of bdagnillo/altair-raytracing: the
+ * multi-bounce trace + observer flux map that the reference's ROOT macros obtain from ROBAST
+ * (AOpticsManager::TraceNonSequential) and then post-process on the host.  The reference has no
+ * FFI of its own; each entry point below names the reference call sites it replaces
+ * (paths relative to the reference repository root).  All structs are plain data, all
+ * pointers are HOST pointers owned by the caller unless the name ends in _dev.  Every function
+ * returns 0 on success or a negative ALTB_E_* code; altb_last_error() gives the message of the
+ * last failure on the calling thread.  There is no CPU fallback: without a CUDA device
+ * altb_create fails with ALTB_E_CUDA.
+ */
+#ifndef ALTAIR_B200_H
+#define ALTAIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALTB_VERSION 1
+
+enum { ALTB_OK = 0, ALTB_E_ARG = -1, ALTB_E_SCENE = -2, ALTB_E_SOURCE = -3, ALTB_E_CUDA = -4, ALTB_E_NOMEM = -5 };
+
+/* ray status, as ARay::IsExited/IsAbsorbed/IsSuspended (fluxAtObserverFast.C:1601-1611) */
+enum { ALTB_EXITED = 1, ALTB_ABSORBED = 2, ALTB_SUSPENDED = 3, ALTB_TAPE_END = 4 };
+
+/* flux-map semantics */
+enum {
+    ALTB_MAP_LINE = 0,             /* Detector::checkIntersection on the true final ray,
+                                      fluxAtObserverOptimize.C:82-119,302-327 */
+    ALTB_MAP_TRACEONCE_COMPAT = 1, /* the map sweepDetectorTraceOnce actually produced: line from the
+                                      origin through the exit point, fluxAtObserverFast.C:1164-1294 */
+    ALTB_MAP_DIRECTION = 2         /* one bin per escaping ray by exit direction (far-field limit) */
+};
+
+/* Scene = what setupOpticsManager builds: fluxAtObserverFast.C:33-41,192-230;
+ * makeIntegratingSphereNRays.C:25-39; integratingSphereDetectorSweep.C:114-123. */
+typedef struct {
+    double r_inner, r_outer;      /* TGeoSphere rmin, rmax [cm] */
+    double theta_max_deg;         /* TGeoSphere theta2: the port is the cone theta > theta_max */
+    double world_half;            /* TGeoBBox half size [cm] */
+    double reflectance;           /* AMirror::SetReflectance */
+    double roughness_rad;         /* ABorderSurfaceCondition::SetGaussianRoughness */
+    int32_t lambertian;           /* EnableLambertian; 0 = specular mirror */
+    int32_t max_bounces;          /* AOpticsManager::SetLimit */
+    int32_t brdf_kind;            /* 0 Lambert; 1 "CustomMirror" = per-bounce spec/diffuse mixture of
+                                     nonLambertianFlux.C:147-208 */
+    int32_t count_all_status;     /* 0: only exited rays can pass the port test (batch macros);
+                                     1: any final status (single-ray macros, makeIntegratingSphereNRays.C:74-78) */
+    double brdf_param[4];         /* kind 1: roughness, specular, diffuse (gBRDF(0.3,0.4,0.6)) */
+    double exit_z;                /* exitPortZ, -100 cm */
+} altb_scene;
+
+/* new ARay(i, lambda, x,y,z, 0, dx,dy,dz): fluxAtObserverFast.C:1147-1150 */
+typedef struct { double pos[3], dir[3]; } altb_source;
+
+/* TH2D fluxMap(n_theta,0,90; n_phi,0,360) + Detector(width,width).setPosition(theta,phi,det_radius):
+ * fluxAtObserverFast.C:1092-1093,1276-1277 */
+typedef struct {
+    int32_t n_theta, n_phi;
+    double det_radius, det_width;
+    int32_t map_mode;
+    int32_t flags;                /* reserved, 0 */
+} altb_map_spec;
+
+typedef struct {
+    uint64_t n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces;
+    double t_trace_s, t_map_s;    /* device time of the trace / map kernels (CUDA events) */
+} altb_stats;
+
+/* Per-ray result = what the macros read back through ARay::GetLastPoint / GetDirection /
+ * GetNpoints / Is*: fluxAtObserverFast.C:298-327,1164-1247. */
+typedef struct { float pos[3]; float dir[3]; uint32_t n_hits; uint32_t status; } altb_record;
+
+typedef struct altb_ctx altb_ctx;
+
+/* devices == NULL: use device 0..n_devices-1 (n_devices <= 0: all visible devices). */
+int  altb_create(altb_ctx** out, const int* devices, int n_devices);
+void altb_destroy(altb_ctx* ctx);
+const char* altb_last_error(void);
+int  altb_version(void);
+int  altb_device_count(void);
+/* batch = rays per trace launch (default 2^26); 0 keeps the default. */
+int  altb_set_batch(altb_ctx* ctx, uint64_t batch_rays);
+
+/* THE HOT PATH.  For each scene: trace rays ray_id0 .. ray_id0+n_rays-1 (ray i's random stream
+ * depends only on (seed, i)) and accumulate the flux map.  counts[n_scenes][n_theta*n_phi] is
+ * theta-major like the CSV rows and is ADDED to.  Replaces TraceNonSequential(ARayArray*) + the
+ * GetExited()/checkIntersection loops: fluxAtObserverOptimize.C:281-333, fluxAtObserverFast.C:1144-1303. */
+int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
+                       uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
+                       uint64_t* counts, altb_stats* stats);
+
+/* Same on device memory of the context's first device, asynchronous on cuda_stream
+ * (a cudaStream_t; NULL = default stream): d_counts[n_scenes][n_bins] uint64 is added to,
+ * d_stats[n_scenes][8] uint64 is added to (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended,
+ * n_bounces, 0, 0).  This is what the multi-GPU driver all-reduces. */
+int altb_trace_fluxmap_dev(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
+                           uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
+                           uint64_t* d_counts, uint64_t* d_stats, void* cuda_stream);
+
+/* Per-ray results.  Replaces TraceNonSequential(ARay&) + GetLastPoint/GetDirection/GetNpoints:
+ * makeIntegratingSphereNRays.C:64-78, distributionSphereDetectorSweep.C:61-99, fluxAtObserver.C:201-223.
+ * Any output pointer may be NULL.  n_points = 1 + hits (+1 for the world-box point of an exited ray). */
+int altb_trace_exit_rays(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                         uint64_t n_rays, uint64_t seed, double* last_pos, double* last_dir,
+                         uint32_t* n_points, uint8_t* status, altb_stats* stats);
+int altb_trace_records(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                       uint64_t n_rays, uint64_t seed, altb_record* records, altb_stats* stats);
+
+/* Physical thin-disk detectors, traced once and tested against all m poses.  Replaces the
+ * per-position re-trace of integratingSphereDetectorSweep.C:31-105,134-172.
+ * det_rot[m][9] row-major TGeoRotation matrices, det_center[m][3]. hits[m] is added to. */
+int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                        uint64_t n_rays, uint64_t seed, const double* det_center, const double* det_rot,
+                        uint32_t m, double det_r, double det_halfthick, uint64_t* hits, altb_stats* stats);
+
+/* Replay mode: ray i starts at ray0[i] = (pos[3], dir[3]) and consumes the recorded draws
+ * tape[8*tape_off[i] .. 8*tape_off[i+1]) (8 f32 per surface hit: u_abs,u_r,u_phi,u_sel,u_psi,g0,g1,u_spare).
+ * bin[i] = direction-map bin of an escaping ray (-1 otherwise) when map != NULL. */
+int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
+                const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map,
+                altb_record* records, int32_t* bin, uint8_t* port);
+
+/* Map stage alone on caller-provided records (host). counts is added to. */
+int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
+                     const altb_record* records, uint64_t n, uint64_t* counts);
+
+/* Counter-based RNG exposed for verification: the 8 draws of hit k for rays ray_id0..+n-1. out[n][8]. */
+int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, float* out);
+
+/* FP32 FFMA-chain throughput of device 0 [TFLOP/s] (roofline denominator measured on the box). */
+int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t altb_launch_count(const altb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
