@@ -144,8 +144,9 @@ def test_replay_bit_exact(ctx, oracle, altb):
     # ragged / perturbed starts and a truncated tape
     rng = np.random.default_rng(1)
     ray0b = ray0.copy()
-    ray0b[:, :3] += rng.uniform(-20, 20, (n, 3))
-    ray0b[:, 3:] = rng.normal(size=(n, 3))
+    v = rng.normal(size=(n, 3))
+    ray0b[:, :3] = v / np.linalg.norm(v, axis=1, keepdims=True) * (95.0 * rng.uniform(0, 1, (n, 1)) ** (1 / 3))
+    ray0b[:, 3:] = rng.normal(size=(n, 3))                       # anywhere inside the cavity, any direction
     off2 = off.copy()
     cut = (off2[1:] - off2[:-1]) > 3
     lens = (off2[1:] - off2[:-1]).astype(np.int64)
