@@ -1,0 +1,63 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/altair_b200.h declares;
+struct layouts agree between the header, the binding and the (independently declared) oracle structs."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "altair_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(altb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(altb):
+    altb.build_library()
+    lib = C.CDLL(altb.library_path())
+    names = _declared_functions()
+    assert len(names) >= 15 and "altb_trace_fluxmap" in names and "altb_replay" in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.altb_version.restype = C.c_int
+    assert lib.altb_version() == 1
+
+
+def test_struct_layouts(altb, oracle):
+    assert C.sizeof(altb.Scene) == C.sizeof(oracle.Scene) == 6 * 8 + 4 * 4 + 4 * 8 + 8
+    assert C.sizeof(altb.Source) == 48 and C.sizeof(altb.MapSpec) == C.sizeof(oracle.MapSpec) == 32
+    assert C.sizeof(altb.Stats) == 64
+    assert altb.RECORD_DTYPE.itemsize == oracle.RECORD_DTYPE.itemsize == 32
+    for (a, _), (b, _) in zip(altb.Scene._fields_, oracle.Scene._fields_):
+        assert a == b and getattr(altb.Scene, a).offset == getattr(oracle.Scene, b).offset
+    # defaults are the reference's constants (fluxAtObserverFast.C:33-41, 199)
+    s = altb.scene()
+    assert (s.r_inner, s.r_outer, s.theta_max_deg, s.world_half) == (100.1, 101.0, 170.0, 300.0)
+    assert (s.reflectance, s.roughness_rad, s.max_bounces, s.exit_z) == (0.99, 0.01, 50000, -100.0)
+
+
+def test_no_cpu_fallback(altb):
+    """Without a CUDA device the product path fails loudly (on a GPU box the context simply works)."""
+    import torch
+    if torch.cuda.is_available():
+        altb.Context().close()
+        return
+    with pytest.raises(altb.AltbError) as e:
+        altb.Context()
+    assert e.value.code == -4 and "no CPU path" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package, include/ or the macros may reference it."""
+    bad = []
+    for base in ("altair-raytracing_b200", "altair_raytracing_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".C")):
+                    t = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"pyoracle|altair_oracle|orc_[a-z]+\(|oracle/", t):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,113 @@
+"""The CPU oracle against the reference's own committed outputs (tests/golden/, built by make_golden.py
+from /root/reference).  Nothing bit-level is pinned by the reference (no tests, no dumped draws; ROOT and
+ROBAST cannot run here), so these are the statistical pins of the "parity unpinned" oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = json.load(open(os.path.join(G, "golden.json")))
+
+
+@pytest.mark.parametrize("theta", [160, 164, 170])
+def test_escape_fraction_matches_reference_footers(oracle, theta):
+    """'# Total rays exiting port: k out of 100000' (fluxAtObserverFast.C:1381) of 5-10 reference runs."""
+    ref = np.array(GOLD["escape_counts"][str(theta)], dtype=float)
+    p_ref, n_ref = ref.sum() / (1e5 * ref.size), 1e5 * ref.size
+    n = 300_000
+    _, st = oracle.trace(oracle.scene(theta_max=float(theta)), oracle.source(), n, seed=2025, prec=oracle.F64,
+                         want_records=False)
+    p = st["n_exit_port"] / n
+    sig = np.sqrt(p_ref * (1 - p_ref) * (1 / n + 1 / n_ref))
+    assert abs(p - p_ref) < 4 * sig, (p, p_ref, sig)
+    assert abs(p / p_ref - 1) < 5e-3
+    assert st["n_exited"] + st["n_absorbed"] + st["n_suspended"] == n
+    # mean bounces per ray = 1/(1 - rho(1 - f)) (finitePort/test.py:11) within 1 %
+    f = (1 - np.cos(np.radians(180 - theta))) / 2
+    assert abs(st["n_bounces"] / n * (1 - 0.99 * (1 - f)) - 1) < 0.012
+
+
+@pytest.mark.parametrize("key,theta", [("170_dir5_0_0", 170.0), ("163_dir5_0_0", 163.0)])
+def test_line_map_matches_per_position_golden(oracle, key, theta):
+    """Semantics A (fluxAtObserverOptimize.C:302-327 + Detector::checkIntersection) bin by bin against the
+    reference's 50 000-rays-per-bin overnight maps."""
+    z = np.load(os.path.join(G, f"perposition_{key}.npz"))
+    k_ref, n_ref = z["hits"].astype(float), float(z["rays_per_bin"])
+    n = 120_000
+    counts, st = oracle.fluxmap(oracle.scene(theta_max=theta), oracle.source(), n, oracle.map_spec(mode=oracle.MAP_LINE),
+                                seed=7, prec=oracle.F64)
+    k = counts.astype(float)
+    p = (k + k_ref) / (n + n_ref)
+    ok = p * (n + n_ref) > 30
+    zz = (k / n - k_ref / n_ref)[ok] / np.sqrt(p[ok] * (1 - p[ok]) * (1 / n + 1 / n_ref))
+    chi2 = (zz ** 2).mean()
+    assert 0.8 < chi2 < 1.25, chi2
+    assert np.abs(zz).max() < 6.0
+    assert abs(zz.mean()) < 0.4      # bins share rays here (trace-once), so the mean is correlated noise
+    # total hits (footer '# Total ray hits') and the on-axis row.  Known residual (DESIGN.md "oracle pins"):
+    # the phi-summed theta profile sits ~2 % below the reference around theta = 25-40 deg and ~1 % above it
+    # beyond 50 deg, i.e. below the reference's own per-bin resolution (3.5-6 % at 50 000 rays/bin).
+    assert abs((k.sum() / n) / (k_ref.sum() / n_ref) - 1) < 0.025
+    prof = k.reshape(180, 90).sum(1).reshape(18, 10).sum(1) / n
+    prof_ref = k_ref.reshape(180, 90).sum(1).reshape(18, 10).sum(1) / n_ref
+    assert np.abs(prof / prof_ref - 1)[:16].max() < 0.05
+    on_axis, on_axis_ref = k[:90].sum() / n / 90, k_ref[:90].sum() / n_ref / 90
+    assert abs(on_axis / on_axis_ref - 1) < 0.05
+
+
+@pytest.mark.parametrize("theta", [160, 170])
+def test_traceonce_compat_matches_published_maps(oracle, theta):
+    """Semantics B: what sweepDetectorTraceOnce actually wrote (fluxAtObserverFast.C:1181 leaves the segment start
+    at the origin).  Best-effort pin: sum of fractions and the on-axis row."""
+    z = np.load(os.path.join(G, f"traceonce_{theta}.npz"))
+    k_ref, n_ref = z["hits"].astype(float), float(z["n_rays"])
+    n = 100_000
+    counts, _ = oracle.fluxmap(oracle.scene(theta_max=float(theta)), oracle.source(), n,
+                               oracle.map_spec(mode=oracle.MAP_TRACEONCE_COMPAT), seed=3, prec=oracle.F64)
+    k = counts.astype(float)
+    assert abs((k.sum() / n) / (k_ref.sum() / n_ref) - 1) < 0.02
+    assert abs((k[:90].sum() / n) / (k_ref[:90].sum() / n_ref) - 1) < 0.04
+    # theta profile (phi-summed rows) agrees within 5 % wherever it is well populated
+    row, row_ref = k.reshape(180, 90).sum(1) / n, k_ref.reshape(180, 90).sum(1) / n_ref
+    big = row_ref > 0.1 * row_ref.max()
+    assert np.abs(row[big] / row_ref[big] - 1).max() < 0.08
+
+
+def test_exit_direction_distribution_matches_raylog(oracle):
+    """distributionSphereDetectorSweep.C:61-99 scene (rho = 1 by default, sigma = 0, box 200, src (-60,0,-80)):
+    3dRayLog.txt / angular_dist.txt hold 100 000 exit directions."""
+    n = 200_000
+    sc = oracle.scene(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000,
+                      count_all_status=1)
+    pos, d, nh, status = oracle.trace_f64(sc, oracle.source((-60, 0, -80), (5, 0, 0)), n, seed=99)
+    assert (status == oracle.EXITED).all()                     # angular_dist.txt sums to exactly 100 000
+    esc = pos[:, 2] < -100.0
+    dz = d[esc, 2]
+    ref = np.array(GOLD["angular_dist"]["counts"], dtype=float)
+    assert ref.sum() == 100000
+    h = np.histogram(dz, bins=100, range=(-1, 1))[0].astype(float)
+    # the reference logged every escaping ray; normalise both to probabilities
+    p_ref, p = ref / ref.sum(), h / h.sum()
+    m = (ref + h) > 40
+    var = p_ref[m] * (1 - p_ref[m]) / ref.sum() + p[m] * (1 - p[m]) / h.sum()
+    chi2 = (((p - p_ref)[m] ** 2) / var).mean()
+    assert chi2 < 1.6, chi2
+    assert abs(dz.mean() - GOLD["raylog"]["mean_dz"]) < 0.004
+    assert dz.max() < 0.0 and abs(dz.max() - GOLD["raylog"]["max_dz"]) < 0.01
+    # independent re-binning of the raw vectors agrees with the reference's own histogram file
+    # (3dRayLog.txt is printed with 6 digits, so values on a bin edge may move by one bin)
+    assert np.abs(np.array(GOLD["raylog"]["dz_hist_100"]) - ref).max() <= 2
+    assert abs(nh.mean() / 131.6 - 1) < 0.03                   # 1/(1-(1-f)) = 131.6 bounces at rho = 1
+
+
+def test_disk_sweep_on_axis_fraction_is_plausible(oracle):
+    """Weak golden: detector_sweep.txt (older run, parameters not recoverable): theta=0 rows mean 0.00275."""
+    sc = oracle.scene(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000)
+    n = 150_000
+    rec, _ = oracle.trace(sc, oracle.source((-60, 0, -80), (5, 0, 0)), n, seed=5, prec=oracle.F64)
+    c, m = oracle.sweep_pose(0.0, 0.0)
+    hits = oracle.disk_hits(sc, rec, c[None, :], m[None, :], 5.0, 0.1)
+    frac = hits[0] / n
+    assert 0.6 * GOLD["detector_sweep_txt"]["theta0_mean_fraction"] < frac < 1.4 * GOLD["detector_sweep_txt"]["theta0_mean_fraction"], frac

@@ -1,0 +1,127 @@
+"""Unit tests of the oracle itself: RNG known answers, the f32 math primitives of the arithmetic contract,
+and how the F32 (kernel-mirror) and F64 (physics) modes relate."""
+import ctypes as C
+
+import numpy as np
+
+
+def test_philox4x32_10_known_answers(oracle):
+    """Random123 kat_vectors for philox4x32-10 (Salmon et al. 2011)."""
+    assert oracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_f32_primitives_accuracy(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    s, c = C.c_float(), C.c_float()
+    worst = 0.0
+    for u in np.concatenate([rng.random(20000, dtype=np.float32), np.float32([0.0, 0.125, 0.25, 0.5, 0.75, 1 - 2 ** -24])]):
+        L.orc_sincos2pi_f32(float(u), C.byref(s), C.byref(c))
+        x = 2 * np.pi * float(u)
+        worst = max(worst, abs(s.value - np.sin(x)), abs(c.value - np.cos(x)))
+    assert worst < 4e-7, worst
+    worst = 0.0
+    for x in rng.uniform(-30, 30, 20000).astype(np.float32):
+        L.orc_sincos_f32(float(x), C.byref(s), C.byref(c))
+        worst = max(worst, abs(s.value - np.sin(float(x))), abs(c.value - np.cos(float(x))))
+    assert worst < 2e-6, worst
+    worst = 0.0
+    for x in np.concatenate([rng.random(20000, dtype=np.float32) + np.float32(2 ** -24), np.float32([2 ** -24, 1.0, 0.5, 0.70710678])]):
+        got = L.orc_log_f32(float(x))
+        worst = max(worst, abs(got - np.log(float(x))) / max(1.0, abs(np.log(float(x)))))
+    assert worst < 3e-7, worst
+
+
+def test_draw_record_distribution(oracle):
+    d = np.stack([oracle.draws(4357, i, k) for i in range(4000) for k in (0, 1, 2, 3, 4)])
+    u = d[:, [0, 1, 2, 3, 4, 7]]
+    assert (u >= 0).all() and (u < 1).all()
+    assert np.abs(u.mean(0) - 0.5).max() < 0.012 and np.abs(u.var(0) - 1 / 12).max() < 0.004
+    for g in (d[:, 5], d[:, 6]):
+        assert abs(g.mean()) < 0.03 and abs(g.var() - 1) < 0.04 and abs((g ** 4).mean() - 3) < 0.3
+    assert abs(np.corrcoef(d[:, 5], d[:, 6])[0, 1]) < 0.03
+    # counter-based: same (seed, ray, k) -> same record; any change -> different record
+    assert np.array_equal(oracle.draws(1, 2, 3), oracle.draws(1, 2, 3))
+    assert not np.array_equal(oracle.draws(1, 2, 3), oracle.draws(1, 2, 4))
+    assert not np.array_equal(oracle.draws(1, 2, 3), oracle.draws(2, 2, 3))
+    assert not np.array_equal(oracle.draws(1, 2, 3), oracle.draws(1, 1 << 32 | 2, 3))
+
+
+def test_f32_and_f64_modes_agree_on_short_chains_and_statistically(oracle):
+    """Same draws in both modes.  Trajectories are chaotic, so per-ray equality can only hold for
+    short chains; the ensembles must agree."""
+    n = 200_000
+    sc, src = oracle.scene(), oracle.source()
+    a, sa = oracle.trace(sc, src, n, seed=21, prec=oracle.F32)
+    b, sb = oracle.trace(sc, src, n, seed=21, prec=oracle.F64)
+    short = b["n_hits"] <= 4
+    assert short.sum() > 5000
+    same = (a["status"] == b["status"]) & (a["n_hits"] == b["n_hits"])
+    assert same[short].mean() > 0.9995
+    both = short & same & (a["status"] == oracle.EXITED)
+    assert np.abs(a["pos"][both] - b["pos"][both]).max() < 0.05          # cm on the world box, f32 rounding only
+    # how fast the two arithmetics decorrelate: agreement drops with chain length
+    long_ = b["n_hits"] >= 60
+    assert same[long_].mean() < same[short].mean()
+    for key in ("n_exit_port", "n_absorbed"):
+        p, q = sa[key] / n, sb[key] / n
+        assert abs(p - q) < 4 * np.sqrt(2 * q * (1 - q) / n) + 1e-9
+    assert abs(sa["n_bounces"] / sb["n_bounces"] - 1) < 5e-3
+
+
+def test_replay_of_own_tape_reproduces_trace(oracle):
+    sc, src = oracle.scene(theta_max=164.0), oracle.source()
+    n = 5000
+    rec, _ = oracle.trace(sc, src, n, seed=5, prec=oracle.F32)
+    tape, off = oracle.make_tape(sc, src, n, seed=5)
+    assert (np.diff(off.astype(np.int64)) == rec["n_hits"]).all()
+    ray0 = np.tile(np.array([-60.0, 0.0, -75.0, 5.0, 0.0, 0.0]), (n, 1))
+    rep = oracle.replay(sc, ray0, tape, off, prec=oracle.F32)
+    assert rep.tobytes() == rec.tobytes()
+    # a truncated tape ends in TAPE_END, an empty one too
+    off2 = off.copy(); off2[1:] = np.minimum(off2[1:], off2[:-1] + 1)
+    off2 = np.concatenate([[0], np.cumsum(np.minimum(np.diff(off.astype(np.int64)), 1))]).astype(np.uint64)
+    idx = off[:-1][np.diff(off.astype(np.int64)) > 0].astype(np.int64)
+    rep2 = oracle.replay(sc, ray0, tape[idx], off2, prec=oracle.F32)
+    assert ((rep2["status"] == oracle.TAPE_END) | (rep2["n_hits"] == 1)).all()
+
+
+def test_map_modes_consistency(oracle):
+    """LINE map: F32 division-free test vs the literal F64 formula differ only for pairs on the disk rim."""
+    sc, src = oracle.scene(), oracle.source()
+    rec, st = oracle.trace(sc, src, 20_000, seed=1, prec=oracle.F32)
+    for mode in (oracle.MAP_LINE, oracle.MAP_TRACEONCE_COMPAT):
+        a = oracle.map_records(sc, oracle.map_spec(mode=mode), rec, prec=oracle.F32).astype(np.int64)
+        b = oracle.map_records(sc, oracle.map_spec(mode=mode), rec, prec=oracle.F64).astype(np.int64)
+        assert a.sum() > 1_000_000
+        assert np.abs(a - b).sum() <= 2e-5 * a.sum()
+    # DIRECTION: one bin per escaping ray with dz < 0
+    d = oracle.map_records(sc, oracle.map_spec(mode=oracle.MAP_DIRECTION), rec)
+    flags = oracle.port_flags(sc, rec)
+    assert d.sum() == (flags & (rec["dir"][:, 2] < 0)).sum() == st["n_exit_port"]
+    # pole / equator / wrap-around bins
+    m = oracle.map_spec(mode=oracle.MAP_DIRECTION)
+    def b(v):
+        v = np.array(v, dtype=np.float32)
+        return oracle.lib().orc_direction_bin(C.byref(m), v.ctypes.data_as(C.POINTER(C.c_float)))
+    assert b([0, 0, -1]) == 0 and b([0, 0, 1]) == -1 and b([1, 0, 0]) == -1
+    assert b([1, 0, -1e-6]) == 179 * 90 and b([1, -1e-6, -1e-6]) == 179 * 90 + 89
+    v = np.array([-1.0, 1e-3, -1.2]) / np.linalg.norm([-1.0, 1e-3, -1.2])
+    th, ph = np.degrees(np.arccos(-v[2])), np.degrees(np.arctan2(v[1], v[0])) % 360
+    assert b(v) == int(th / 0.5) * 90 + int(ph / 4.0) and b(v) % 90 == 44
+
+
+def test_detector_pose_is_the_references_misoriented_normal(oracle):
+    """Detector::setPosition (fluxAtObserverFast.C:61-80): normal = (-dy, dx, dz)/|d|, not the radial direction."""
+    p, n = (C.c_double * 3)(), (C.c_double * 3)()
+    oracle.lib().orc_detector_pose(30.0, 90.0, 100.0, p, n)
+    assert np.allclose(list(p), [0.0, 50.0, -100 - 100 * np.cos(np.radians(30))], atol=1e-9)
+    assert np.allclose(list(n), [-0.5, 0.0, -np.cos(np.radians(30))], atol=1e-9)
+    # a vertical line through the detector centre hits, one 21 cm away in the plane misses (width 40)
+    L, v = (C.c_double * 3)(0.0, 50.0, 0.0), (C.c_double * 3)(0.0, 0.0, -1.0)
+    assert oracle.lib().orc_detector_hit(p, n, 40.0, L, v) == 1
+    L2 = (C.c_double * 3)(0.0, 71.1, 0.0)
+    assert oracle.lib().orc_detector_hit(p, n, 40.0, L2, v) == 0
