@@ -165,12 +165,12 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
 
 template <bool R, int M>
 static void launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
-    k_trace<R, M><<<blocks, 256, 0, st>>>(P, rec, counter);
+    k_trace<R, M><<<blocks, TRACE_THREADS, 0, st>>>(P, rec, counter);
 }
 
 static int trace_blocks_per_sm(bool rough, int model) {
     int b = 0;
-#define OCC(R, M) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<R, M>, 256, 0)
+#define OCC(R, M) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<R, M>, TRACE_THREADS, 0)
     if (rough) { if (model == 0) OCC(true, 0); else if (model == 1) OCC(true, 1); else OCC(true, 2); }
     else       { if (model == 0) OCC(false, 0); else if (model == 1) OCC(false, 1); else OCC(false, 2); }
 #undef OCC

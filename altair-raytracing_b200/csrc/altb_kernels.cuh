@@ -29,8 +29,13 @@ __device__ __forceinline__ void store_record(altb_record* __restrict__ rec, uint
     p[1] = make_float4(s.dir.y, s.dir.z, __uint_as_float(s.hits), __uint_as_float((uint32_t)status));
 }
 
-// One surface hit.  Returns 0 to continue or the final status.
-template <bool ROUGH, int MODEL>
+// Status codes internal to the kernels: the ray crossed the inner sphere inside the port opening and
+// its fate (edge hit or exit) is decided by the double-precision slow path.
+static constexpr int ST_CROSSING = 100;
+
+// One surface hit.  Returns 0 to continue, a final ALTB_* status, or ST_CROSSING with
+// s.pos = the crossing point and s.dir = the new direction (DEFER_CROSSING only).
+template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
 __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayState& s, const Draws& dr) {
     s.hits += 1;
     f3 nrm;
@@ -49,8 +54,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
         float m = -2.0f * dot3(s.dir, n);
         d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
     } else if (MODEL == 1) {
-        if (dr.u_sel < k.p_spec) d = brdf_spec(n, s.dir, dr.g1, dr.u_phi, k.brdf_s);
-        else d = brdf_diff(n, dr.u_r, dr.u_phi);
+        d = brdf_mix(n, s.dir, dr.u_sel < k.p_spec, dr.u_r, dr.g1, dr.u_phi, k.brdf_s);
     } else {
         d = lambert_dir(n, dr.u_r, dr.u_phi);
     }
@@ -63,34 +67,55 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
     if (s.hits >= (uint32_t)g.max_bounces) { s.dir = d; return ALTB_SUSPENDED; }
     int kind;
     double out[3];
-    const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
     if (s.where == EV_WALL) {
         float t = k.two_r1 * dn;
         f3 x = {fma_(t, d.x, s.pos.x), fma_(t, d.y, s.pos.y), fma_(t, d.z, s.pos.z)};
         float sc = fma_(dot3(x, x), k.nr_c, 1.5f);
         x.x *= sc; x.y *= sc; x.z *= sc;
-        if (x.z >= k.zc) { s.pos = x; s.dir = d; return 0; }        // fast path: wall to wall
+        s.pos = x; s.dir = d;
+        if (x.z >= k.zc) return 0;                                   // fast path: wall to wall
+        if (DEFER_CROSSING) return ST_CROSSING;
         const double xd[3] = {(double)x.x, (double)x.y, (double)x.z};
+        const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
         kind = cap_crossing(g, xd, dd, out);
     } else {
         const double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z};
+        const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
         kind = from_edge(g, q, dd, out);
+        s.dir = d;
     }
     s.pos.x = (float)out[0]; s.pos.y = (float)out[1]; s.pos.z = (float)out[2];
-    s.dir = d;
     if (kind == EV_EXIT) return ALTB_EXITED;
     s.where = kind;
     return 0;
 }
 
 // ------------------------------------------------------------------------------------ K1
+// Persistent warps.  Every lane owns one live ray; a lane whose ray ends takes the next ray at once
+// (first from the warp's resume queue, then from ids claimed in chunks off one global counter), so the
+// bounce body always runs with ~all 32 lanes.  The rare double-precision work -- a ray crossing the port
+// opening: cone-edge test + world-box exit -- is not done in line (it would run with ~1 active lane in
+// every fifth iteration): the lane parks (crossing point, direction, id, hits) in the warp's shared-memory
+// queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
+// turn out to hit the port edge (4 % of them) come back through the resume queue.
+static constexpr int TRACE_THREADS = 256;
+static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
+static constexpr int QCAP = 64;                     // entries per queue per warp (32 pending + 32 new)
+
+struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
+
 template <bool ROUGH, int MODEL>
-__global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TraceParams P,
-                                               altb_record* __restrict__ rec,
-                                               unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const __grid_constant__ TraceParams P,
+                                                         altb_record* __restrict__ rec,
+                                                         unsigned int* __restrict__ counter) {
     constexpr bool NEED_B = ROUGH || MODEL == 1;
-    const unsigned lane = threadIdx.x & 31u;
+    __shared__ QEntry s_xq[TRACE_WARPS][QCAP];      // crossings waiting for the slow path
+    __shared__ QEntry s_rq[TRACE_WARPS][QCAP];      // rays to resume (edge / wall events found by the slow path)
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    QEntry* xq = s_xq[warp];
+    QEntry* rq = s_rq[warp];
+    uint32_t nx = 0, nr = 0;          // warp-uniform queue fills
     uint32_t next = 0, end = 0;       // warp-uniform: ids [next,end) are claimed by this warp
     bool exhausted = false;           // warp-uniform: the global pool is empty
     bool alive = false;
@@ -101,9 +126,24 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
     const f3 d_start = {(float)P.d0[0], (float)P.d0[1], (float)P.d0[2]};
 
     while (true) {
-        const unsigned need = __ballot_sync(FULL, !alive);
+        // ---- regeneration
+        unsigned need = __ballot_sync(FULL, !alive);
         if (need) {
-            if (!exhausted) {
+            if (nr) {                                   // resume parked rays first
+                const uint32_t rank = __popc(need & lt_mask);
+                if (!alive && rank < nr) {
+                    const QEntry e = rq[nr - 1 - rank];
+                    s.pos = {e.a.x, e.a.y, e.a.z}; s.dir = {e.a.w, e.b.x, e.b.y};
+                    idx = __float_as_uint(e.b.z);
+                    const uint32_t hw = __float_as_uint(e.b.w);
+                    s.hits = hw & 0x7fffffffu; s.where = (hw >> 31) ? EV_EDGE : EV_WALL;
+                    alive = true;
+                }
+                nr -= min(nr, (uint32_t)__popc(need));
+                __syncwarp();
+                need = __ballot_sync(FULL, !alive);
+            }
+            if (need && !exhausted) {
                 if (next >= end) {
                     uint32_t base = 0;
                     if (lane == 0) base = atomicAdd(counter, P.chunk);
@@ -120,13 +160,59 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
                 }
                 next = min(end, next + (uint32_t)__popc(need));
             }
-            if (exhausted && !__any_sync(FULL, alive)) break;
         }
+        const bool any_alive = __any_sync(FULL, alive);
+        if (!any_alive && exhausted && nx == 0 && nr == 0) break;
+
+        // ---- one surface hit per live lane
+        bool crossing = false;
         if (alive) {
             Draws dr;
             make_draws<NEED_B>(P.seed, P.ray_id0 + idx, s.hits, dr);
-            const int st = bounce_step<ROUGH, MODEL>(P.g, P.k, s, dr);
-            if (st) { store_record(rec, idx, s, st); alive = false; }
+            const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
+            if (st == ST_CROSSING) { crossing = true; alive = false; }
+            else if (st) { store_record(rec, idx, s, st); alive = false; }
+        }
+        const unsigned cm = __ballot_sync(FULL, crossing);
+        if (cm) {
+            if (crossing) {
+                QEntry e;
+                e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
+                e.b = make_float4(s.dir.y, s.dir.z, __uint_as_float(idx), __uint_as_float(s.hits));
+                xq[nx + __popc(cm & lt_mask)] = e;
+            }
+            nx += __popc(cm);
+            __syncwarp();
+        }
+        // ---- drain the crossing queue at full width (or whatever is left once nothing else can run)
+        if (nx >= 32 || (nx && !any_alive && exhausted && nr == 0)) {
+            const uint32_t take = min(nx, 32u);
+            const uint32_t base = nx - take;
+            bool resume = false;
+            QEntry e;
+            if (lane < take) {
+                e = xq[base + lane];
+                const double xd[3] = {(double)e.a.x, (double)e.a.y, (double)e.a.z};
+                const double dd[3] = {(double)e.a.w, (double)e.b.x, (double)e.b.y};
+                double out[3];
+                const int kind = cap_crossing(P.g, xd, dd, out);
+                e.a.x = (float)out[0]; e.a.y = (float)out[1]; e.a.z = (float)out[2];
+                if (kind == EV_EXIT) {
+                    float4* p = reinterpret_cast<float4*>(rec + __float_as_uint(e.b.z));
+                    p[0] = e.a;
+                    p[1] = make_float4(e.b.x, e.b.y, e.b.w, __uint_as_float((uint32_t)ALTB_EXITED));
+                } else {
+                    resume = true;
+                    if (kind == EV_EDGE) e.b.w = __uint_as_float(__float_as_uint(e.b.w) | 0x80000000u);
+                }
+            }
+            nx = base;
+            const unsigned rm = __ballot_sync(FULL, resume);
+            if (rm) {
+                if (resume) rq[nr + __popc(rm & lt_mask)] = e;
+                nr += __popc(rm);
+            }
+            __syncwarp();
         }
     }
 }
@@ -169,7 +255,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         Draws dr;
         dr.u_abs = a.x; dr.u_r = a.y; dr.u_phi = a.z; dr.u_sel = a.w;
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
-        st = bounce_step<ROUGH, MODEL>(P.g, P.k, s, dr);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, s, dr);
     }
     store_record(rec, i, s, st);
 }
