@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libaltair_b200.so")
+_LIB_PATH = os.environ.get("ALTB_LIB") or os.path.join(_PKG, "libaltair_b200.so")   # ALTB_LIB: experiment builds
 
 EXITED, ABSORBED, SUSPENDED, TAPE_END = 1, 2, 3, 4
 MAP_LINE, MAP_TRACEONCE_COMPAT, MAP_DIRECTION = 0, 1, 2

@@ -98,6 +98,9 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
 // every fifth iteration): the lane parks (crossing point, direction, id, hits) in the warp's shared-memory
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
 // turn out to hit the port edge (4 % of them) come back through the resume queue.
+#ifndef ALTB_TRACE_MINB
+#define ALTB_TRACE_MINB 3
+#endif
 static constexpr int TRACE_THREADS = 256;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 static constexpr int QCAP = 64;                     // entries per queue per warp (32 pending + 32 new)
@@ -105,10 +108,10 @@ static constexpr int QCAP = 64;                     // entries per queue per war
 struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
 
 template <bool ROUGH, int MODEL>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const __grid_constant__ TraceParams P,
+__global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const __grid_constant__ TraceParams P,
                                                          altb_record* __restrict__ rec,
                                                          unsigned int* __restrict__ counter) {
-    constexpr bool NEED_B = ROUGH || MODEL == 1;
+    constexpr bool NEED_G = ROUGH || MODEL == 1;
     __shared__ QEntry s_xq[TRACE_WARPS][QCAP];      // crossings waiting for the slow path
     __shared__ QEntry s_rq[TRACE_WARPS][QCAP];      // rays to resume (edge / wall events found by the slow path)
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const __grid_constant__
         bool crossing = false;
         if (alive) {
             Draws dr;
-            make_draws<NEED_B>(P.seed, P.ray_id0 + idx, s.hits, dr);
+            make_draws<NEED_G>(P.seed, P.ray_id0 + idx, s.hits, dr);
             const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
             if (st == ST_CROSSING) { crossing = true; alive = false; }
             else if (st) { store_record(rec, idx, s, st); alive = false; }

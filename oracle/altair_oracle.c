@@ -231,23 +231,28 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline float u01(uint32_t w) { return (float)(w >> 8) * 0x1p-24f; }
-
+/* ONE Philox4x32-10 block (128 bits) per surface hit, counter = (ray_id lo, ray_id hi, k, 0), key = seed:
+ *   w0: u_abs 24 b | 8 b -> bm_u1      w1: u_r 24 b | 8 b -> bm_u1
+ *   w2: u_phi 20 b | 8 b -> u_sel | 4 b -> bm_u1
+ *   w3: u_psi 13 b | bm_u2 13 b | 6 b -> u_sel
+ * (g0, g1) = Box-Muller of (bm_u1 in (0,1] with 20 bits, bm_u2 with 13 bits). */
 void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, 0u};
-    uint32_t a[4], b[4];
-    orc_philox4x32_10(ctr, key, a);
-    ctr[3] = 1u;
-    orc_philox4x32_10(ctr, key, b);
-    out[0] = u01(a[0]); out[1] = u01(a[1]); out[2] = u01(a[2]); out[3] = u01(a[3]);
-    out[4] = u01(b[0]);
-    float u1 = (float)((b[1] >> 8) + 1u) * 0x1p-24f;       /* (0,1] */
+    uint32_t w[4];
+    orc_philox4x32_10(ctr, key, w);
+    out[0] = (float)(w[0] >> 8) * 0x1p-24f;
+    out[1] = (float)(w[1] >> 8) * 0x1p-24f;
+    out[2] = (float)(w[2] >> 12) * 0x1p-20f;
+    out[3] = (float)(((w[3] & 0x3fu) << 8) | ((w[2] >> 4) & 0xffu)) * 0x1p-14f;
+    out[4] = (float)(w[3] >> 19) * 0x1p-13f;
+    uint32_t t = ((w[0] & 0xffu) << 12) | ((w[1] & 0xffu) << 4) | (w[2] & 0xfu);
+    float u1 = (float)(t + 1u) * 0x1p-20f;                 /* (0,1] */
     float rad = sqrtf(-2.0f * orc_log_f32(u1));
     float s, c;
-    orc_sincos2pi_f32(u01(b[2]), &s, &c);
+    orc_sincos2pi_f32((float)((w[3] >> 6) & 0x1fffu) * 0x1p-13f, &s, &c);
     out[5] = rad * c; out[6] = rad * s;
-    out[7] = u01(b[3]);
+    out[7] = 0.0f;
 }
 
 /* ------------------------------------------------------------------ the two instantiations */

@@ -82,9 +82,9 @@ enum { ORC_F64 = 0, ORC_F32 = 1 };
 
 #define ORC_DRAWS_PER_HIT 8
 /* draw record of one surface hit (f32):
- *   [0] u_abs  [1] u_r  [2] u_phi  [3] u_sel      <- Philox block A  (counter word3 = 0)
- *   [4] u_psi  [5] g0   [6] g1     [7] u_spare    <- Philox block B  (counter word3 = 1)
- * u_* uniform on [0,1) with 24 bits; g0,g1 independent N(0,1) (Box-Muller of B.y,B.z). */
+ *   [0] u_abs  [1] u_r  [2] u_phi  [3] u_sel  [4] u_psi  [5] g0  [6] g1  [7] reserved (0)
+ * all derived from ONE Philox4x32-10 block per hit (bit budget in altair_oracle.c:orc_draws);
+ * u_* uniform on [0,1); g0,g1 independent N(0,1) (Box-Muller). */
 
 /* Philox4x32-10 (Salmon et al. 2011), one block. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

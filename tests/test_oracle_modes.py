@@ -37,9 +37,12 @@ def test_f32_primitives_accuracy(oracle):
 
 def test_draw_record_distribution(oracle):
     d = np.stack([oracle.draws(4357, i, k) for i in range(4000) for k in (0, 1, 2, 3, 4)])
-    u = d[:, [0, 1, 2, 3, 4, 7]]
-    assert (u >= 0).all() and (u < 1).all()
+    u = d[:, [0, 1, 2, 3, 4]]
+    assert (u >= 0).all() and (u < 1).all() and (d[:, 7] == 0).all()
     assert np.abs(u.mean(0) - 0.5).max() < 0.012 and np.abs(u.var(0) - 1 / 12).max() < 0.004
+    # all seven values come from ONE Philox block: fields cut from the same word must not correlate
+    cc = np.corrcoef(d[:, :7].T)
+    assert np.abs(cc - np.eye(7)).max() < 0.03
     for g in (d[:, 5], d[:, 6]):
         assert abs(g.mean()) < 0.03 and abs(g.var() - 1) < 0.04 and abs((g ** 4).mean() - 3) < 0.3
     assert abs(np.corrcoef(d[:, 5], d[:, 6])[0, 1]) < 0.03
