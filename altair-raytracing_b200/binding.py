@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.environ.get("ALTB_LIB") or os.path.join(_PKG, "libaltair_b200.so")   # ALTB_LIB: experiment builds
 
 EXITED, ABSORBED, SUSPENDED, TAPE_END = 1, 2, 3, 4
-MAP_LINE, MAP_TRACEONCE_COMPAT, MAP_DIRECTION = 0, 1, 2
+MAP_LINE, MAP_TRACEONCE_COMPAT, MAP_DIRECTION, MAP_PER_POSITION, MAP_TWOFOLD = 0, 1, 2, 3, 4
 
 RECORD_DTYPE = np.dtype([("pos", "<f4", 3), ("dir", "<f4", 3), ("n_hits", "<u4"), ("status", "<u4")])
 
@@ -38,7 +38,7 @@ class Source(C.Structure):
 
 class MapSpec(C.Structure):
     _fields_ = [("n_theta", C.c_int32), ("n_phi", C.c_int32), ("det_radius", C.c_double),
-                ("det_width", C.c_double), ("map_mode", C.c_int32), ("flags", C.c_int32)]
+                ("det_width", C.c_double), ("map_mode", C.c_int32), ("rays_per_position", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -71,9 +71,9 @@ def source(pos=(-60.0, 0.0, -75.0), direction=(5.0, 0.0, 0.0)):
     return s
 
 
-def map_spec(n_theta=180, n_phi=90, det_radius=100.0, det_width=40.0, mode=MAP_LINE):
+def map_spec(n_theta=180, n_phi=90, det_radius=100.0, det_width=40.0, mode=MAP_LINE, rays_per_position=0):
     m = MapSpec()
-    m.n_theta, m.n_phi, m.det_radius, m.det_width, m.map_mode, m.flags = n_theta, n_phi, det_radius, det_width, mode, 0
+    m.n_theta, m.n_phi, m.det_radius, m.det_width, m.map_mode, m.rays_per_position = n_theta, n_phi, det_radius, det_width, mode, rays_per_position
     return m
 
 

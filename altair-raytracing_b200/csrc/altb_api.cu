@@ -222,11 +222,14 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     (void)sc;
     if (map->n_theta < 1 || map->n_phi < 1 || (int64_t)map->n_theta * map->n_phi > (1 << 24))
         return fail(ALTB_E_ARG, "map: bad bin counts %d x %d", map->n_theta, map->n_phi);
-    if (map->map_mode < ALTB_MAP_LINE || map->map_mode > ALTB_MAP_DIRECTION) return fail(ALTB_E_ARG, "map: bad map_mode %d", map->map_mode);
+    if (map->map_mode < ALTB_MAP_LINE || map->map_mode > ALTB_MAP_TWOFOLD) return fail(ALTB_E_ARG, "map: bad map_mode %d", map->map_mode);
+    const bool grouped = map->map_mode == ALTB_MAP_PER_POSITION || map->map_mode == ALTB_MAP_TWOFOLD;
+    if (grouped && map->rays_per_position < 1) return fail(ALTB_E_ARG, "map: rays_per_position must be >= 1");
+    if (map->map_mode == ALTB_MAP_TWOFOLD && (map->n_phi & 1)) return fail(ALTB_E_ARG, "map: twofold needs an even n_phi");
     MapParams& M = ms.M;
     memset(&M, 0, sizeof M);
     const int nt = map->n_theta, np = map->n_phi;
-    M.n_theta = nt; M.n_phi = np; M.mode = map->map_mode;
+    M.n_theta = nt; M.n_phi = np; M.mode = map->map_mode; M.rays_per_position = map->rays_per_position;
     M.count_all = g.count_all; M.exit_zf = k.exit_zf;
     const double hw = map->det_width / 2;
     M.w2 = (float)(hw * hw);
@@ -235,6 +238,7 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     if (!M.use_smem_hist) ms.dir_smem = 0;
     ms.n_tiles = 0; ms.line_smem = 0;
     if (map->map_mode == ALTB_MAP_DIRECTION) return 0;
+    (void)grouped;
     if (!(map->det_radius > 0) || !(map->det_width > 0)) return fail(ALTB_E_ARG, "map: det_radius/det_width must be > 0");
 
     // per-row / per-column tables (Detector::setPosition, fluxAtObserverFast.C:61-80), rounded once to f32
@@ -307,7 +311,7 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
 }
 
 // records d.rec[0..n) -> counts (+stats)
-static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, unsigned long long* d_counts,
+static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uint64_t ray_base, unsigned long long* d_counts,
                    unsigned long long* d_stats, int* d_bin, cudaStream_t st) {
     if (n == 0) return 0;
     const MapParams& M = ms.M;
@@ -332,6 +336,15 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uns
         k_stats<<<blocks, 256, 0, st>>>(d.rec, n, M.count_all, M.exit_zf, d_stats);
         ctx->launches++;
         CK(cudaGetLastError());
+    }
+    if (M.mode == ALTB_MAP_PER_POSITION || M.mode == ALTB_MAP_TWOFOLD) {
+        int blocks = d.sm_count * 8;
+        const int need = (int)((n + 255) / 256);
+        if (blocks > need) blocks = need;
+        k_map_per_position<<<blocks, 256, 0, st>>>(d.rec, n, M, (unsigned long long)ray_base, d_counts);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
     }
     static bool attr_line = false;
     if (!attr_line) {
@@ -370,7 +383,7 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
             if (t_trace_ms) CK(cudaEventRecord(d.ev[0], st));
             if (int rc = run_trace(ctx, d, ts, ray_id0 + off, n, st)) return rc;
             if (t_trace_ms) CK(cudaEventRecord(d.ev[1], st));
-            if (int rc = run_map(ctx, d, ms, n, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, st)) return rc;
+            if (int rc = run_map(ctx, d, ms, n, ray_id0 + off, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, st)) return rc;
             if (t_trace_ms) {
                 CK(cudaEventRecord(d.ev[2], st));
                 CK(cudaEventSynchronize(d.ev[2]));
@@ -522,7 +535,7 @@ extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const al
     for (uint64_t off = 0; off < n; off += batch) {
         const uint32_t m = (uint32_t)std::min<uint64_t>(batch, n - off);
         CK(cudaMemcpyAsync(d.rec, records + off, (size_t)m * sizeof(altb_record), cudaMemcpyHostToDevice, d.stream));
-        if (int rc = run_map(ctx, d, ms, m, d.counts, nullptr, nullptr, d.stream)) return rc;
+        if (int rc = run_map(ctx, d, ms, m, off, d.counts, nullptr, nullptr, d.stream)) return rc;
     }
     std::vector<unsigned long long> host(nb);
     CK(cudaMemcpyAsync(host.data(), d.counts, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));

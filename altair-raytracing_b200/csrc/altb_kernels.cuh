@@ -275,6 +275,7 @@ struct MapParams {
     const float4* tiles;           // [n_tiles]: bounding-sphere centre, (w + r_tile + margin)^2
     int t_theta, t_phi, nt_theta, nt_phi;                                // tile shape / tile grid
     int use_smem_hist;
+    int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
 };
 
 __device__ __forceinline__ void load_record(const altb_record* __restrict__ rec, size_t i, f3& pos, f3& dir,
@@ -492,6 +493,36 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const altb_record* __
             if (inb && acc) atomicAdd(counts + (size_t)i * M.n_phi + j, (unsigned long long)acc);
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2c per-position maps
+// The reference's production mode traces FRESH rays for every detector position
+// (fluxAtObserverOptimize.C:542-579: 50 000 rays per (theta,phi)); the twofold variant shares each batch
+// between the two positions 180 deg apart (fluxAtObserverFast.C:336-408,660-720).  Ray id r belongs to
+// group r / rays_per_position and is tested only against that group's position(s).
+__global__ void __launch_bounds__(256) k_map_per_position(const altb_record* __restrict__ rec, uint32_t n,
+                                                          const MapParams M, unsigned long long ray_base,
+                                                          unsigned long long* __restrict__ counts) {
+    const int half = M.n_phi / 2;
+    const unsigned long long n_groups = M.mode == ALTB_MAP_TWOFOLD ? (unsigned long long)M.n_theta * half
+                                                                   : (unsigned long long)M.n_theta * M.n_phi;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (size_t)gridDim.x * blockDim.x) {
+        f3 pos, dir; uint32_t hits, status;
+        load_record(rec, r, pos, dir, hits, status);
+        if (!port_flag(M.count_all, M.exit_zf, pos, status)) continue;
+        const unsigned long long g = (ray_base + r) / (unsigned long long)M.rays_per_position;
+        if (g >= n_groups) continue;
+        int i, j;
+        if (M.mode == ALTB_MAP_TWOFOLD) { i = (int)(g / half); j = (int)(g % half); }
+        else { i = (int)(g / M.n_phi); j = (int)(g % M.n_phi); }
+        if (line_hit(M.rs[i], M.pz[i], M.st[i], M.ct[i], M.cp[j], M.sp[j], M.w2, pos, dir))
+            atomicAdd(counts + (size_t)i * M.n_phi + j, 1ull);
+        if (M.mode == ALTB_MAP_TWOFOLD) {
+            const int j2 = j + half;
+            if (line_hit(M.rs[i], M.pz[i], M.st[i], M.ct[i], M.cp[j2], M.sp[j2], M.w2, pos, dir))
+                atomicAdd(counts + (size_t)i * M.n_phi + j2, 1ull);
+        }
     }
 }
 

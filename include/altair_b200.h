@@ -33,7 +33,11 @@ enum {
                                       fluxAtObserverOptimize.C:82-119,302-327 */
     ALTB_MAP_TRACEONCE_COMPAT = 1, /* the map sweepDetectorTraceOnce actually produced: line from the
                                       origin through the exit point, fluxAtObserverFast.C:1164-1294 */
-    ALTB_MAP_DIRECTION = 2         /* one bin per escaping ray by exit direction (far-field limit) */
+    ALTB_MAP_DIRECTION = 2,        /* one bin per escaping ray by exit direction (far-field limit) */
+    ALTB_MAP_PER_POSITION = 3,     /* LINE test with FRESH rays per detector position: ray id r belongs to position
+                                      r / rays_per_position (theta-major), fluxAtObserverOptimize.C:542-579 */
+    ALTB_MAP_TWOFOLD = 4           /* as PER_POSITION, each batch shared by (theta,phi) and (theta,phi+180):
+                                      group g = i*(n_phi/2)+j, fluxAtObserverFast.C:336-408,660-720 */
 };
 
 /* Scene = what setupOpticsManager builds: fluxAtObserverFast.C:33-41,192-230;
@@ -63,7 +67,7 @@ typedef struct {
     int32_t n_theta, n_phi;
     double det_radius, det_width;
     int32_t map_mode;
-    int32_t flags;                /* reserved, 0 */
+    int32_t rays_per_position;    /* modes PER_POSITION / TWOFOLD (int n = 50000); otherwise ignored */
 } altb_map_spec;
 
 typedef struct {

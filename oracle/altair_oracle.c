@@ -563,10 +563,39 @@ static inline int line_hit_f32(const map_tab_f* t, int i, int j, const float* L,
 
 int orc_map_records(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n,
                     int prec, uint64_t* counts, int n_threads) {
+    return orc_map_records_at(sc, map, rec, n, 0, prec, counts, n_threads);
+}
+
+int orc_map_records_at(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n, uint64_t ray_base,
+                       int prec, uint64_t* counts, int n_threads) {
     geom g; consts_f kf; consts_d kd;
     if (make_geom(sc, &g, &kf, &kd)) return -1;
     int nt = map->n_theta, np = map->n_phi, nb = nt * np;
     if (nt < 1 || np < 1) return -1;
+    if (map->map_mode == ORC_MAP_PER_POSITION || map->map_mode == ORC_MAP_TWOFOLD) {
+        int two = map->map_mode == ORC_MAP_TWOFOLD, half = np / 2;
+        if (map->rays_per_position < 1 || (two && (np & 1))) return -1;
+        uint64_t n_groups = two ? (uint64_t)nt * half : (uint64_t)nb;
+        map_tab_f tab; make_tab_f(map, &tab);
+        for (uint64_t r = 0; r < n; r++) {
+            if (!port_flag_g(&g, rec[r].pos, rec[r].status)) continue;
+            uint64_t grp = (ray_base + r) / (uint64_t)map->rays_per_position;
+            if (grp >= n_groups) continue;
+            int i = two ? (int)(grp / half) : (int)(grp / np), j = two ? (int)(grp % half) : (int)(grp % np);
+            for (int rep = 0; rep < (two ? 2 : 1); rep++, j += half) {
+                int hit;
+                if (prec == ORC_F32) hit = line_hit_f32(&tab, i, j, rec[r].pos, rec[r].dir);
+                else {
+                    double p[3], nn[3], L[3] = {rec[r].pos[0], rec[r].pos[1], rec[r].pos[2]}, v[3] = {rec[r].dir[0], rec[r].dir[1], rec[r].dir[2]};
+                    orc_detector_pose((i + 0.5) * 90.0 / nt, (j + 0.5) * 360.0 / np, map->det_radius, p, nn);
+                    hit = orc_detector_hit(p, nn, map->det_width, L, v);
+                }
+                counts[(size_t)i * np + j] += (uint64_t)hit;
+            }
+        }
+        free_tab_f(&tab);
+        return 0;
+    }
     if (map->map_mode == ORC_MAP_DIRECTION) {
         for (uint64_t r = 0; r < n; r++) {
             if (!port_flag_g(&g, rec[r].pos, rec[r].status)) continue;
@@ -637,7 +666,7 @@ int orc_fluxmap(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, ui
         uint64_t m = n - off < chunk ? n - off : chunk;
         orc_stats s;
         rc = orc_trace(sc, src, ray_id0 + off, m, seed, prec, rec, &s, n_threads);
-        if (!rc) rc = orc_map_records(sc, map, rec, m, prec, counts, n_threads);
+        if (!rc) rc = orc_map_records_at(sc, map, rec, m, ray_id0 + off, prec, counts, n_threads);
         tot.n_rays += s.n_rays; tot.n_exited += s.n_exited; tot.n_exit_port += s.n_exit_port;
         tot.n_absorbed += s.n_absorbed; tot.n_suspended += s.n_suspended; tot.n_bounces += s.n_bounces;
     }

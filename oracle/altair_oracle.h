@@ -64,8 +64,8 @@ typedef struct { double pos[3], dir[3]; } orc_source;
 typedef struct {
     int32_t n_theta, n_phi;
     double det_radius, det_width;
-    int32_t map_mode;      /* 0 LINE, 1 TRACEONCE_COMPAT, 2 DIRECTION */
-    int32_t pad_;
+    int32_t map_mode;      /* 0 LINE, 1 TRACEONCE_COMPAT, 2 DIRECTION, 3 PER_POSITION, 4 TWOFOLD */
+    int32_t rays_per_position;
 } orc_map_spec;
 
 typedef struct {
@@ -77,7 +77,7 @@ typedef struct {
 typedef struct { float pos[3]; float dir[3]; uint32_t n_hits; uint32_t status; } orc_record;
 
 enum { ORC_EXITED = 1, ORC_ABSORBED = 2, ORC_SUSPENDED = 3, ORC_TAPE_END = 4 };
-enum { ORC_MAP_LINE = 0, ORC_MAP_TRACEONCE_COMPAT = 1, ORC_MAP_DIRECTION = 2 };
+enum { ORC_MAP_LINE = 0, ORC_MAP_TRACEONCE_COMPAT = 1, ORC_MAP_DIRECTION = 2, ORC_MAP_PER_POSITION = 3, ORC_MAP_TWOFOLD = 4 };
 enum { ORC_F64 = 0, ORC_F32 = 1 };
 
 #define ORC_DRAWS_PER_HIT 8
@@ -123,6 +123,10 @@ int orc_port_flag(const orc_scene* sc, const orc_record* r);
  * formula in double; ORC_F32 = the kernels' division-free f32 form).  Brute force. */
 int orc_map_records(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n,
                     int prec, uint64_t* counts, int n_threads);
+/* same with the ray id of rec[0] (needed by the PER_POSITION / TWOFOLD modes: fluxAtObserverOptimize.C:542-579,
+ * fluxAtObserverFast.C:660-720: ray id r is tested only against position group r / rays_per_position) */
+int orc_map_records_at(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n, uint64_t ray_base,
+                       int prec, uint64_t* counts, int n_threads);
 int32_t orc_direction_bin(const orc_map_spec* map, const float d[3]);
 
 /* trace + map in one go (chunked; multi-threaded when n_threads != 1; <= 0 -> all cores). */

@@ -1,0 +1,128 @@
+"""The macro mirror end to end on the GPU: same entry points as the reference's ROOT macros, outputs checked
+against the oracle and against the reference's file formats."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "altair-raytracing_b200")
+
+
+@pytest.fixture(scope="module")
+def M(altb, tmp_path_factory):
+    C.CDLL(altb.library_path(), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(os.path.join(PKG, "libaltair_macros.so"))
+    d = C.c_double
+    for name in ("altbm_sweepDetector", "altbm_sweepDetectorTwofold", "altbm_sweepDetectorTraceOnce"):
+        getattr(L, name).argtypes = [C.c_int, C.c_char_p, C.c_int, d, d, d, d, d, d, d]
+    L.altbm_set.argtypes = [C.c_char_p, d]
+    L.altbm_last_csv.restype = C.c_char_p
+    L.altbm_last_count.restype = C.c_longlong
+    L.altbm_last_hist.restype = d
+    L.altbm_last_fluxmap.restype = d
+    out = tmp_path_factory.mktemp("macros")
+    L.altbm_set_output_dir(str(out).encode())
+    L.altbm_set(b"verbose", 0)
+    L.out = str(out)
+    return L
+
+
+def _rows(path):
+    return np.array([[float(x) for x in l.split(",")] for l in open(path) if l[0].isdigit()])
+
+
+def test_sweepDetectorTraceOnce(M, oracle):
+    M.altbm_set(b"traceonce_rays", 20000)
+    for shipped, mode in ((1, oracle.MAP_TRACEONCE_COMPAT), (0, oracle.MAP_LINE)):
+        M.altbm_set(b"traceonce_as_shipped", shipped)
+        M.altbm_sweepDetectorTraceOnce(0, b"res", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 164.0)
+        path = M.altbm_last_csv().decode()
+        assert os.path.basename(path).startswith("fluxmap_traceonce_20000rays_180x90_src-60_0_-75")
+        rows = _rows(path)
+        counts, st = oracle.fluxmap(oracle.scene(theta_max=164.0), oracle.source(), 20000, oracle.map_spec(mode=mode), seed=4357,
+                                    prec=oracle.F32)
+        assert np.array_equal(np.rint(rows[:, 2] * 20000).astype(np.uint64), counts)
+        text = open(path).read()
+        assert f"# Total rays exiting port: {st['n_exit_port']} out of 20000" in text
+        assert "# Exit port angle: 164 degrees" in text and "# Ray tracing time:" in text and "# Detector sweep time:" in text
+        assert M.altbm_last_fluxmap(1, 1) == counts[0] / 20000
+    # the second run did not overwrite the first (getUniqueFilename)
+    assert path.endswith("_1.csv")
+    M.altbm_set(b"traceonce_as_shipped", 1)
+    M.altbm_set(b"traceonce_rays", 100000)
+
+
+def test_sweepDetector_per_position_and_twofold(M, oracle):
+    M.altbm_set(b"rays_per_position", 300)
+    M.altbm_set(b"n_theta_bins", 36); M.altbm_set(b"n_phi_bins", 18)
+    try:
+        M.altbm_sweepDetector(0, b"pp", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+        path = M.altbm_last_csv().decode()
+        rows = _rows(path)
+        mp = oracle.map_spec(36, 18, 100.0, 40.0, oracle.MAP_PER_POSITION, rays_per_position=300)
+        counts, st = oracle.fluxmap(oracle.scene(), oracle.source(), 36 * 18 * 300, mp, seed=4357, prec=oracle.F32)
+        assert counts.sum() > 0 and np.array_equal(np.rint(rows[:, 2] * 300).astype(np.uint64), counts)
+        assert f"# Total ray hits: {counts.sum()} out of {36 * 18 * 300}" in open(path).read()
+        assert M.altbm_last_count(b"totalHitRays") == counts.sum()
+        M.altbm_sweepDetectorTwofold(0, b"pp", 1, -60.0, 0.0, -75.0, 5.0, 2.0, 0.0, 170.0)
+        rows = _rows(M.altbm_last_csv().decode())
+        mp = oracle.map_spec(36, 18, 100.0, 40.0, oracle.MAP_TWOFOLD, rays_per_position=300)
+        counts, _ = oracle.fluxmap(oracle.scene(), oracle.source(direction=(5.0, 2.0, 0.0)), 36 * 9 * 300, mp, seed=4357, prec=oracle.F32)
+        got = np.zeros(36 * 18, dtype=np.uint64)
+        for th, ph, fr in rows:
+            got[int(th / 2.5) * 18 + int(ph / 20.0)] = round(fr * 300)
+        assert np.array_equal(got, counts) and counts.sum() > 0
+    finally:
+        M.altbm_set(b"rays_per_position", 50000); M.altbm_set(b"n_theta_bins", 180); M.altbm_set(b"n_phi_bins", 90)
+
+
+def test_makeIntegratingSphereNRays_and_distribution(M, oracle):
+    M.altbm_set(b"nrays_macro", 50000)                      # BASELINE.json config C1
+    M.altbm_makeIntegratingSphereNRays()
+    sc = oracle.scene(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000, count_all_status=1)
+    src = oracle.source((-60, 0, -80), (5, 0, 0))
+    _, st = oracle.trace(sc, src, 50000, seed=4357, prec=oracle.F32, want_records=False)
+    assert M.altbm_last_count(b"fluxCount") == st["n_exit_port"] and st["n_exit_port"] > 49900
+    assert M.altbm_last_count(b"n_bounces") == st["n_bounces"]
+    M.altbm_set(b"distribution_rays", 30000)
+    M.altbm_distributionSphereDetectorSweep()
+    rec, _ = oracle.trace(sc, src, 30000, seed=4357, prec=oracle.F32)
+    esc = rec["pos"][:, 2] < -100.0
+    dz = rec["dir"][esc].astype(np.float64)
+    dz = dz[:, 2] / np.linalg.norm(dz, axis=1)
+    h = np.histogram(dz, bins=100, range=(-1, 1))[0]
+    got = np.array([M.altbm_last_hist(b"hDirectionZ", b) for b in range(1, 101)])
+    assert np.abs(got - h).sum() <= 2 and got.sum() == esc.sum()        # (bin-edge ties in double vs numpy)
+    assert M.altbm_last_count(b"fluxCount") == esc.sum()
+    # as written in the reference, theta = sign(dx)*acos(dz) lies outside (-90,90): everything overflows (:94,48-50)
+    assert sum(M.altbm_last_hist(b"hAngularDist", b) for b in range(1, 181)) == 0
+
+
+def test_integratingSphereDetectorSweep(M, oracle):
+    M.altbm_set(b"sweep_rays", 40000); M.altbm_set(b"sweep_dtheta", 5.0)
+    M.altbm_integratingSphereDetectorSweep()
+    path = M.altbm_last_csv().decode()
+    lines = open(path).read().splitlines()
+    assert lines[0] == "Theta(deg)\tPhi(deg)\tHitFraction" and len(lines) == 1 + 19 * 2
+    sc = oracle.scene(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000, count_all_status=1)
+    rec, _ = oracle.trace(sc, oracle.source((-60, 0, -80), (5, 0, 0)), 40000, seed=4357, prec=oracle.F32)
+    poses = [oracle.sweep_pose(t, p) for t in np.arange(-45, 45.01, 5.0) for p in (0.0, 180.0)]
+    hits = oracle.disk_hits(sc, rec, np.array([c for c, _ in poses]), np.array([m for _, m in poses]), 5.0, 0.1)
+    got = np.array([float(l.split("\t")[2]) for l in lines[1:]])
+    assert np.allclose(got, hits / 40000, atol=1e-9) and hits.sum() > 0
+    M.altbm_set(b"sweep_rays", 100000); M.altbm_set(b"sweep_dtheta", 0.5)
+
+
+def test_cli_runner(M, altb):
+    exe = os.path.join(PKG, "altb_macro")
+    out = subprocess.run([exe, "makeIntegratingSphereNRays.C"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "Flux of rays through the exit port: 1000" in out.stdout or "Flux of rays through the exit port: 999" in out.stdout
+    out = subprocess.run([exe, "nonLambertianFlux.C", "--set", "nonlambertian_rays=200", "--set", "verbose=0", "--out", M.out],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    rows = _rows(os.path.join(M.out, "fluxmap_data.csv"))
+    assert rows.shape == (900, 3) and rows[:, 2].sum() > 0 and open(os.path.join(M.out, "fluxmap_data.csv")).readline() == "theta,phi,fraction\n"

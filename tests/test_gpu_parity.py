@@ -96,6 +96,24 @@ def test_fluxmap_small_odd_grid_and_batches(ctx, oracle, altb):
     assert g_st[0]["n_bounces"] == o_st["n_bounces"]
 
 
+@pytest.mark.parametrize("mode", ["PER_POSITION", "TWOFOLD"])
+def test_per_position_modes_bit_exact(ctx, oracle, altb, mode):
+    """Fresh rays per detector position (fluxAtObserverOptimize.C:542-579) / shared by a 180-deg pair (Fast.C:660-720)."""
+    rpp, nt, npb = 700, 30, 12
+    groups = nt * npb if mode == "PER_POSITION" else nt * npb // 2
+    n = groups * rpp + 123                                   # trailing rays beyond the last group are ignored
+    gm = altb.map_spec(nt, npb, 100.0, 40.0, getattr(altb, "MAP_" + mode), rays_per_position=rpp)
+    om = oracle.map_spec(nt, npb, 100.0, 40.0, getattr(oracle, "MAP_" + mode), rays_per_position=rpp)
+    ctx.set_batch(50_001)                                    # groups straddle batch boundaries
+    try:
+        g_counts, g_st = ctx.trace_fluxmap(altb.scene(), altb.source(), n, gm, seed=SEED)
+    finally:
+        ctx.set_batch(0)
+    o_counts, o_st = oracle.fluxmap(oracle.scene(), oracle.source(), n, om, seed=SEED, prec=oracle.F32)
+    assert np.array_equal(g_counts[0], o_counts) and o_counts.sum() > 100
+    assert g_st[0]["n_bounces"] == o_st["n_bounces"]
+
+
 def test_multi_scene_and_empty(ctx, oracle, altb):
     thetas = (160.0, 164.0, 175.0)
     gm = altb.map_spec(mode=altb.MAP_DIRECTION)
