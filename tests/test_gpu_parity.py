@@ -179,6 +179,25 @@ def test_replay_bit_exact(ctx, oracle, altb):
     assert (g2["status"] == altb.TAPE_END).sum() > 0
 
 
+def test_replay_against_double_precision_oracle(ctx, oracle, altb):
+    """North-star replay criterion: feed recorded initial rays + draws, compare the FP32 GPU result with the
+    DOUBLE-PRECISION oracle per ray: escape port flag, status and bin index exact, except <= 1e-4 of the rays."""
+    n = 200_000
+    for kw in (dict(theta_max=170.0), dict(theta_max=164.0, brdf_kind=1)):
+        tape, off = oracle.make_tape(oracle.scene(**kw), oracle.source(), n, seed=2)
+        ray0 = np.tile(np.array([-60.0, 0.0, -75.0, 5.0, 0.0, 0.0]), (n, 1))
+        ref = oracle.replay(oracle.scene(**kw), ray0, tape, off, prec=oracle.F64)
+        g_rec, g_bin, g_port = ctx.replay(altb.scene(**kw), ray0, tape, off, altb.map_spec(mode=altb.MAP_DIRECTION))
+        ref_port = oracle.port_flags(oracle.scene(**kw), ref)
+        import ctypes as C
+        om = oracle.map_spec(mode=oracle.MAP_DIRECTION)
+        ref_bin = np.array([oracle.lib().orc_direction_bin(C.byref(om), r["dir"].ctypes.data_as(C.POINTER(C.c_float)))
+                            if p else -1 for r, p in zip(ref, ref_port)], dtype=np.int32)
+        bad = (g_rec["status"] != ref["status"]) | (g_port.astype(bool) != ref_port) | (g_bin != ref_bin)
+        assert bad.mean() <= 1e-4, (kw, bad.mean())
+        assert (g_rec["status"] == altb.TAPE_END).sum() <= bad.sum()
+
+
 def test_detector_sweep_bit_exact(ctx, oracle, altb):
     kw = dict(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000)
     poses = [oracle.sweep_pose(t, p) for t in np.arange(-45, 45.01, 2.5) for p in (0.0, 180.0)]

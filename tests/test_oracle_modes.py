@@ -53,26 +53,29 @@ def test_draw_record_distribution(oracle):
     assert not np.array_equal(oracle.draws(1, 2, 3), oracle.draws(1, 1 << 32 | 2, 3))
 
 
-def test_f32_and_f64_modes_agree_on_short_chains_and_statistically(oracle):
-    """Same draws in both modes.  Trajectories are chaotic, so per-ray equality can only hold for
-    short chains; the ensembles must agree."""
-    n = 200_000
+def test_f32_and_f64_modes_agree_per_ray(oracle):
+    """The north-star's replay criterion between the two arithmetics of the oracle: same draws, per-ray escape
+    port / status / bin equal except <= 1e-4 of the rays (those within FP32 epsilon of a boundary).  Rounding
+    differences do not grow along a trajectory: the end-point error is independent of the chain length."""
+    n = 300_000
     sc, src = oracle.scene(), oracle.source()
     a, sa = oracle.trace(sc, src, n, seed=21, prec=oracle.F32)
     b, sb = oracle.trace(sc, src, n, seed=21, prec=oracle.F64)
-    short = b["n_hits"] <= 4
-    assert short.sum() > 5000
     same = (a["status"] == b["status"]) & (a["n_hits"] == b["n_hits"])
-    assert same[short].mean() > 0.9995
-    both = short & same & (a["status"] == oracle.EXITED)
-    assert np.abs(a["pos"][both] - b["pos"][both]).max() < 0.05          # cm on the world box, f32 rounding only
-    # how fast the two arithmetics decorrelate: agreement drops with chain length
-    long_ = b["n_hits"] >= 60
-    assert same[long_].mean() < same[short].mean()
-    for key in ("n_exit_port", "n_absorbed"):
-        p, q = sa[key] / n, sb[key] / n
-        assert abs(p - q) < 4 * np.sqrt(2 * q * (1 - q) / n) + 1e-9
-    assert abs(sa["n_bounces"] / sb["n_bounces"] - 1) < 5e-3
+    assert 1 - same.mean() <= 1e-4, 1 - same.mean()
+    assert (oracle.port_flags(sc, a) != oracle.port_flags(sc, b)).mean() <= 1e-4
+    ex = same & (a["status"] == oracle.EXITED)
+    dpos = np.abs(a["pos"][ex] - b["pos"][ex]).max(1)
+    ddir = np.abs(a["dir"][ex] - b["dir"][ex]).max(1)
+    assert dpos.max() < 0.05 and np.median(ddir) < 1e-6 and ddir.max() < 1e-3
+    long_, short = b["n_hits"][ex] >= 150, b["n_hits"][ex] <= 10
+    assert long_.sum() > 1000 and np.median(ddir[long_]) < 3 * np.median(ddir[short]) + 1e-7     # no growth
+    m = oracle.map_spec(mode=oracle.MAP_DIRECTION)
+    ca = oracle.map_records(sc, m, a).astype(np.int64)
+    cb = oracle.map_records(sc, m, b).astype(np.int64)
+    assert np.abs(ca - cb).sum() <= 2e-4 * cb.sum()                        # a moved ray changes two bins
+    for key in ("n_exit_port", "n_absorbed", "n_bounces"):
+        assert abs(sa[key] / sb[key] - 1) < 1e-4
 
 
 def test_replay_of_own_tape_reproduces_trace(oracle):
