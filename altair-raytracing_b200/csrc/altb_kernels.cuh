@@ -47,14 +47,16 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
         nrm.x = (float)nn[0]; nrm.y = (float)nn[1]; nrm.z = (float)nn[2];
     }
     if (k.rho < dr.u_abs) return ALTB_ABSORBED;
-    f3 n = nrm;
-    if (ROUGH) n = tilt_normal(nrm, dr.u_psi, dr.g0, k.sigma);
+    f3 n = nrm, t1, t2;
+    if (ROUGH) tilt_normal(nrm, dr.u_psi, dr.g0, k.sigma, n, t1, t2);
     f3 d;
     if (MODEL == 2) {
         float m = -2.0f * dot3(s.dir, n);
         d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
     } else if (MODEL == 1) {
         d = brdf_mix(n, s.dir, dr.u_sel < k.p_spec, dr.u_r, dr.g1, dr.u_phi, k.brdf_s);
+    } else if (ROUGH) {
+        d = lambert_in(n, t1, t2, dr.u_r, dr.u_phi);
     } else {
         d = lambert_dir(n, dr.u_r, dr.u_phi);
     }

@@ -63,12 +63,12 @@ def test_traceonce_compat_matches_published_maps(oracle, theta):
     at the origin).  Best-effort pin: sum of fractions and the on-axis row."""
     z = np.load(os.path.join(G, f"traceonce_{theta}.npz"))
     k_ref, n_ref = z["hits"].astype(float), float(z["n_rays"])
-    n = 100_000
+    n = 300_000       # the ~90 on-axis positions nearly coincide, so that row has the statistics of ONE bin
     counts, _ = oracle.fluxmap(oracle.scene(theta_max=float(theta)), oracle.source(), n,
                                oracle.map_spec(mode=oracle.MAP_TRACEONCE_COMPAT), seed=3, prec=oracle.F64)
     k = counts.astype(float)
     assert abs((k.sum() / n) / (k_ref.sum() / n_ref) - 1) < 0.02
-    assert abs((k[:90].sum() / n) / (k_ref[:90].sum() / n_ref) - 1) < 0.04
+    assert abs((k[:90].sum() / n) / (k_ref[:90].sum() / n_ref) - 1) < 0.05
     # theta profile (phi-summed rows) agrees within 5 % wherever it is well populated
     row, row_ref = k.reshape(180, 90).sum(1) / n, k_ref.reshape(180, 90).sum(1) / n_ref
     big = row_ref > 0.1 * row_ref.max()
