@@ -157,7 +157,7 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
     const int kind0 = launch_ray(ts.P.g, src->pos, src->dir, ts.P.d0, ts.P.x0);
     if (kind0 < 0) return fail(ALTB_E_SOURCE, "source must lie strictly inside the inner sphere with a non-zero direction");
     ts.P.kind0 = kind0;
-    ts.P.seed = seed;
+    ts.P.keys = philox_expand(seed);
     ts.rough = sc->roughness_rad != 0.0;
     ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : 0);
     return 0;
@@ -668,7 +668,7 @@ extern "C" int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64
     CK(cudaSetDevice(d.dev));
     float* buf = nullptr;
     CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
-    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(seed, ray_id0, (uint32_t)n, k, buf);
+    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), ray_id0, (uint32_t)n, k, buf);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out, buf, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);

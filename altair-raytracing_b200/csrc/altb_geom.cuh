@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "altb_math.cuh"
+
 #define ALTB_HD __host__ __device__ __forceinline__
 
 namespace altb {
@@ -27,7 +29,7 @@ struct TraceParams {
     int kind0;            // first event of the (identical) source rays
     double x0[3];         // its point
     double d0[3];         // unit source direction
-    uint64_t seed;
+    PhiloxKeys keys;      // round keys of the seed
     uint64_t ray_id0;     // global id of local ray 0
     uint32_t n;           // rays in this launch
     uint32_t chunk;       // ids a warp claims at a time

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const 
         bool crossing = false;
         if (alive) {
             Draws dr;
-            make_draws<NEED_G>(P.seed, P.ray_id0 + idx, s.hits, dr);
+            make_draws<NEED_G>(P.keys, P.ray_id0 + idx, s.hits, dr);
             const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
             if (st == ST_CROSSING) { crossing = true; alive = false; }
             else if (st) { store_record(rec, idx, s, st); alive = false; }
@@ -588,11 +588,11 @@ __global__ void __launch_bounds__(256) k_disk_hits(const altb_record* __restrict
 }
 
 // ------------------------------------------------------------------------------------ RNG probe
-__global__ void k_draws(uint64_t seed, uint64_t ray_id0, uint32_t n, uint32_t k, float* __restrict__ out) {
+__global__ void k_draws(const __grid_constant__ PhiloxKeys K, uint64_t ray_id0, uint32_t n, uint32_t k, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Draws d;
-    make_draws<true>(seed, ray_id0 + i, k, d);
+    make_draws<true>(K, ray_id0 + i, k, d);
     float4* o = reinterpret_cast<float4*>(out + 8 * (size_t)i);
     o[0] = make_float4(d.u_abs, d.u_r, d.u_phi, d.u_sel);
     o[1] = make_float4(d.u_psi, d.g0, d.g1, d.u_spare);
