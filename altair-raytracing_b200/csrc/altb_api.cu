@@ -34,6 +34,7 @@ struct DevCtx {
     unsigned long long* stats = nullptr;      // [8]
     float* tables = nullptr; uint64_t tables_cap = 0;   // floats
     float4* tiles = nullptr; uint64_t tiles_cap = 0;
+    float4* lines = nullptr; uint64_t lines_cap = 0;    // dense list of escaping rays for the line maps (2 float4 each)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -88,7 +89,7 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         if (d.dev < 0) continue;
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles);
+        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines);
         for (auto& e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -266,6 +267,20 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     const int shapes[6][2] = {{32, 1}, {16, 2}, {8, 4}, {4, 8}, {2, 16}, {1, 32}};
     double best = 1e300; int bt = 8, bp = 4;
     std::vector<float4> best_tiles;
+    auto bound = [&](int i0, int i1, int j0, int j1) {     // bounding sphere of the detector centres of bins [i0,i1) x [j0,j1)
+        double cx = 0, cy = 0, cz = 0; int cnt = 0;
+        for (int i = i0; i < i1; i++)
+            for (int j = j0; j < j1; j++) { cx += px[(size_t)i * np + j]; cy += py[(size_t)i * np + j]; cz += pzv[(size_t)i * np + j]; cnt++; }
+        cx /= cnt; cy /= cnt; cz /= cnt;
+        double r = 0;
+        for (int i = i0; i < i1; i++)
+            for (int j = j0; j < j1; j++) {
+                const double dx = px[(size_t)i * np + j] - cx, dy = py[(size_t)i * np + j] - cy, dz = pzv[(size_t)i * np + j] - cz;
+                r = std::max(r, sqrt(dx * dx + dy * dy + dz * dz));
+            }
+        const double rad = hw + r + 0.5;     // conservative: disk radius + tile radius + f32 slack [cm]
+        return make_float4((float)cx, (float)cy, (float)cz, (float)(rad * rad * 1.0001));
+    };
     for (auto& s : shapes) {
         const int tt = s[0], tp = s[1];
         const int ntt = (nt + tt - 1) / tt, ntp = (np + tp - 1) / tp;
@@ -296,8 +311,12 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     M.t_theta = bt; M.t_phi = bp;
     M.nt_theta = (nt + bt - 1) / bt; M.nt_phi = (np + bp - 1) / bp;
     ms.n_tiles = M.nt_theta * M.nt_phi;
-    ms.line_smem = (size_t)LINE_BATCH * 6 * sizeof(float) + (size_t)ms.n_tiles * LINE_WORDS * sizeof(uint32_t) +
-                   ((size_t)4 * nt + 2 * np) * sizeof(float);
+    const int nst = (M.nt_theta + SUPER - 1) / SUPER, nsp = (M.nt_phi + SUPER - 1) / SUPER;
+    for (int a = 0; a < nst; a++)
+        for (int b = 0; b < nsp; b++)
+            best_tiles.push_back(bound(a * SUPER * bt, std::min(nt, (a + 1) * SUPER * bt), b * SUPER * bp, std::min(np, (b + 1) * SUPER * bp)));
+    ms.line_smem = (size_t)LINE_BATCH * 2 * sizeof(float4) + (size_t)ms.n_tiles * LINE_WORDS * sizeof(uint32_t) +
+                   (size_t)(ms.n_tiles + nst * nsp) * sizeof(float4) + (size_t)nst * nsp * sizeof(uint32_t) + ((size_t)4 * nt + 2 * np) * sizeof(float);
     if (ms.line_smem > 200 * 1024) return fail(ALTB_E_ARG, "map: %d x %d bins need %zu B of shared memory", nt, np, ms.line_smem);
     if (int rc = ensure(d.tables, d.tables_cap, (uint64_t)tab.size())) return rc;
     if (int rc = ensure(d.tiles, d.tiles_cap, (uint64_t)best_tiles.size())) return rc;
@@ -306,7 +325,7 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     CK(cudaStreamSynchronize(st));   // the host vectors die at return
     M.rs = d.tables; M.pz = d.tables + nt; M.st = d.tables + 2 * nt; M.ct = d.tables + 3 * nt;
     M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
-    M.tiles = d.tiles;
+    M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
     return 0;
 }
 
@@ -346,18 +365,25 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
         CK(cudaGetLastError());
         return 0;
     }
-    static bool attr_line = false;
-    if (!attr_line) {
-        CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_line = true;
+    CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;
+    CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
+    {
+        int cb = d.sm_count * 8;
+        const int need = (int)((n + 255) / 256);
+        if (cb > need) cb = need;
+        k_compact_exits<<<cb, 256, 0, st>>>(d.rec, n, M, d.lines, d.counter);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
     int per_sm = (int)((220 * 1024) / (ms.line_smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    const int by_threads = 2048 / LINE_THREADS;
+    if (per_sm > by_threads) per_sm = by_threads;
     int blocks = d.sm_count * per_sm;
     const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
     if (blocks > need) blocks = need;
-    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.rec, n, M, d_counts);
+    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.lines, d.counter, M, d_counts);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

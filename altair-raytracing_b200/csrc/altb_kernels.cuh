@@ -105,7 +105,10 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
 #endif
 static constexpr int TRACE_THREADS = 256;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
-static constexpr int QCAP = 64;                     // entries per queue per warp (32 pending + 32 new)
+#ifndef ALTB_BOUNCES_PER_CHECK
+#define ALTB_BOUNCES_PER_CHECK 1
+#endif
+static constexpr int QCAP = 32 + 32 * ALTB_BOUNCES_PER_CHECK;   // entries per queue per warp (pending + new per check)
 
 struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
 
@@ -169,25 +172,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const 
         const bool any_alive = __any_sync(FULL, alive);
         if (!any_alive && exhausted && nx == 0 && nr == 0) break;
 
-        // ---- one surface hit per live lane
-        bool crossing = false;
-        if (alive) {
-            Draws dr;
-            make_draws<NEED_G>(P.keys, P.ray_id0 + idx, s.hits, dr);
-            const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
-            if (st == ST_CROSSING) { crossing = true; alive = false; }
-            else if (st) { store_record(rec, idx, s, st); alive = false; }
-        }
-        const unsigned cm = __ballot_sync(FULL, crossing);
-        if (cm) {
-            if (crossing) {
-                QEntry e;
-                e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
-                e.b = make_float4(s.dir.y, s.dir.z, __uint_as_float(idx), __uint_as_float(s.hits));
-                xq[nx + __popc(cm & lt_mask)] = e;
+        // ---- ALTB_BOUNCES_PER_CHECK surface hits per live lane between two regeneration checks
+#pragma unroll
+        for (int rep = 0; rep < ALTB_BOUNCES_PER_CHECK; rep++) {
+            bool crossing = false;
+            if (alive) {
+                Draws dr;
+                make_draws<NEED_G>(P.keys, P.ray_id0 + idx, s.hits, dr);
+                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
+                if (st == ST_CROSSING) { crossing = true; alive = false; }
+                else if (st) { store_record(rec, idx, s, st); alive = false; }
             }
-            nx += __popc(cm);
-            __syncwarp();
+            const unsigned cm = __ballot_sync(FULL, crossing);
+            if (cm) {
+                if (crossing) {
+                    QEntry e;
+                    e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
+                    e.b = make_float4(s.dir.y, s.dir.z, __uint_as_float(idx), __uint_as_float(s.hits));
+                    xq[nx + __popc(cm & lt_mask)] = e;
+                }
+                nx += __popc(cm);
+                __syncwarp();
+            }
         }
         // ---- drain the crossing queue at full width (or whatever is left once nothing else can run)
         if (nx >= 32 || (nx && !any_alive && exhausted && nr == 0)) {
@@ -275,6 +281,7 @@ struct MapParams {
     const float* rs; const float* pz; const float* st; const float* ct;   // [n_theta]
     const float* cp; const float* sp;                                     // [n_phi]
     const float4* tiles;           // [n_tiles]: bounding-sphere centre, (w + r_tile + margin)^2
+    const float4* supers;          // [n_super]: same for blocks of SUPER x SUPER tiles
     int t_theta, t_phi, nt_theta, nt_phi;                                // tile shape / tile grid
     int use_smem_hist;
     int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
@@ -396,105 +403,148 @@ __device__ __forceinline__ bool line_hit(float rs, float pz, float st, float ct,
     return (fabsf(dot) >= 1e-10f) && (r2 <= w2 * (dot * dot));
 }
 
-static constexpr int LINE_BATCH = 512;      // exit rays staged per block pass
+#ifndef ALTB_LINE_BATCH
+#define ALTB_LINE_BATCH 512
+#endif
+#ifndef ALTB_LINE_THREADS
+#define ALTB_LINE_THREADS 512
+#endif
+static constexpr int LINE_BATCH = ALTB_LINE_BATCH;      // exit rays per block pass (multiple of 32)
 static constexpr int LINE_WORDS = LINE_BATCH / 32;
-static constexpr int LINE_THREADS = 256;
+static constexpr int LINE_THREADS = ALTB_LINE_THREADS;
+static constexpr int SUPER = 4;             // a super-tile is SUPER x SUPER tiles
 
-// dynamic shared memory layout: float rays[LINE_BATCH][6]; uint32 bitmap[n_tiles][LINE_WORDS]; tables
-__global__ void __launch_bounds__(LINE_THREADS) k_map_line(const altb_record* __restrict__ rec, uint32_t n,
-                                                           const MapParams M,
+// records -> dense list of the escaping rays' test lines (L.xyz, v.x | v.yz, 0, 0); order is irrelevant
+// (integer counts).  TRACEONCE_COMPAT: the line from the origin through the exit point (fluxAtObserverFast.C:1181).
+__global__ void __launch_bounds__(256) k_compact_exits(const altb_record* __restrict__ rec, uint32_t n, const MapParams M,
+                                                       float4* __restrict__ lines, unsigned int* __restrict__ n_lines) {
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool pf = false; f3 pos, dir; uint32_t hits, status;
+        if (i < n) {
+            load_record(rec, i, pos, dir, hits, status);
+            pf = port_flag(M.count_all, M.exit_zf, pos, status);
+        }
+        const unsigned m = __ballot_sync(FULL, pf);
+        unsigned base = 0;
+        if (lane == 0 && m) base = atomicAdd(n_lines, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (pf) {
+            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+            f3 L, v;
+            if (M.mode == ALTB_MAP_TRACEONCE_COMPAT) {
+                const float inv = 1.0f / sqrtf(dot3(pos, pos));
+                L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
+            } else { L = pos; v = dir; }
+            lines[2 * (size_t)slot] = make_float4(L.x, L.y, L.z, v.x);
+            lines[2 * (size_t)slot + 1] = make_float4(v.y, v.z, 0.f, 0.f);
+        }
+    }
+}
+
+// dynamic shared memory layout:
+//   float4 rays[LINE_BATCH][2]; uint32 bitmap[n_tiles][LINE_WORDS]; float4 tiles[n_tiles]; float4 supers[n_super];
+//   uint32 sup_ij[n_super]; tables
+__global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restrict__ lines,
+                                                           const unsigned int* __restrict__ n_lines_ptr, const MapParams M,
                                                            unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_tiles = M.nt_theta * M.nt_phi;
-    float* rays = reinterpret_cast<float*>(smem_raw);                        // [LINE_BATCH*6]
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(rays + LINE_BATCH * 6);     // [n_tiles*LINE_WORDS]
-    float* t_rs = reinterpret_cast<float*>(bitmap + (size_t)n_tiles * LINE_WORDS);
+    const int ns_theta = (M.nt_theta + SUPER - 1) / SUPER, ns_phi = (M.nt_phi + SUPER - 1) / SUPER;
+    const int n_super = ns_theta * ns_phi;
+    float4* rays = reinterpret_cast<float4*>(smem_raw);                          // [LINE_BATCH*2]
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(rays + LINE_BATCH * 2);       // [n_tiles*LINE_WORDS]
+    float4* s_tiles = reinterpret_cast<float4*>(bitmap + (size_t)n_tiles * LINE_WORDS);
+    float4* s_super = s_tiles + n_tiles;
+    uint32_t* s_sup_ij = reinterpret_cast<uint32_t*>(s_super + n_super);          // first tile (ti << 16 | tj) of each super-tile
+    float* t_rs = reinterpret_cast<float*>(s_sup_ij + n_super);
     float* t_pz = t_rs + M.n_theta; float* t_st = t_pz + M.n_theta; float* t_ct = t_st + M.n_theta;
     float* t_cp = t_ct + M.n_theta; float* t_sp = t_cp + M.n_phi;
-    __shared__ int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = LINE_THREADS / 32;
 
     for (int i = tid; i < M.n_theta; i += LINE_THREADS) { t_rs[i] = M.rs[i]; t_pz[i] = M.pz[i]; t_st[i] = M.st[i]; t_ct[i] = M.ct[i]; }
     for (int j = tid; j < M.n_phi; j += LINE_THREADS) { t_cp[j] = M.cp[j]; t_sp[j] = M.sp[j]; }
+    for (int t = tid; t < n_tiles; t += LINE_THREADS) s_tiles[t] = M.tiles[t];
+    for (int t = tid; t < n_super; t += LINE_THREADS) {
+        s_super[t] = M.supers[t];
+        s_sup_ij[t] = (uint32_t)((t / ns_phi) * SUPER) << 16 | (uint32_t)((t % ns_phi) * SUPER);
+    }
+    const size_t n_lines = *n_lines_ptr;
+    const int li = lane / M.t_phi, lj = lane % M.t_phi;
 
-    // each block owns a contiguous slab of records and walks it in passes that fill LINE_BATCH exit rays
-    const size_t slab = ((size_t)n + gridDim.x - 1) / gridDim.x;
-    size_t cur = (size_t)blockIdx.x * slab;
-    const size_t stop = min((size_t)n, cur + slab);
-
-    while (cur < stop) {
-        if (tid == 0) s_count = 0;
-        __syncthreads();
-        // ---- stage: compact escaping rays of the next records into shared memory (order-independent)
-        size_t taken = 0;
-        while (cur + taken < stop) {
-            // stop early enough that one more sweep of LINE_THREADS records cannot overflow
-            if (s_count > LINE_BATCH - LINE_THREADS) break;
-            const size_t i = cur + taken + tid;
-            bool pf = false; f3 pos, dir; uint32_t hits, status;
-            if (i < stop) {
-                load_record(rec, i, pos, dir, hits, status);
-                pf = port_flag(M.count_all, M.exit_zf, pos, status);
-            }
-            const unsigned m = __ballot_sync(FULL, pf);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_count, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-            if (pf) {
-                const int slot = base + __popc(m & ((1u << lane) - 1u));
-                f3 L, v;
-                if (M.mode == ALTB_MAP_TRACEONCE_COMPAT) {
-                    const float inv = 1.0f / sqrtf(dot3(pos, pos));
-                    L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
-                } else { L = pos; v = dir; }
-                float* r = rays + slot * 6;
-                r[0] = L.x; r[1] = L.y; r[2] = L.z; r[3] = v.x; r[4] = v.y; r[5] = v.z;
-            }
-            taken += LINE_THREADS;
-            __syncthreads();
-        }
-        cur = min(stop, cur + taken);
-        const int nr = s_count;
+    for (size_t cur = (size_t)blockIdx.x * LINE_BATCH; cur < n_lines; cur += (size_t)gridDim.x * LINE_BATCH) {
+        const int nr = (int)min((size_t)LINE_BATCH, n_lines - cur);
         const int nwords = (nr + 31) >> 5;
-        // ---- phase 1: conservative tile culling, one ray per lane, bitmap[tile][word]
-        for (int w = warp; w < nwords; w += NW) {
-            const int r = w * 32 + lane;
-            const bool valid = r < nr;
-            f3 L = {0.f, 0.f, 0.f}, v = {0.f, 0.f, 1.f};
-            if (valid) { const float* p = rays + r * 6; L = {p[0], p[1], p[2]}; v = {p[3], p[4], p[5]}; }
-            for (int t = 0; t < n_tiles; t++) {
-                const float4 c = M.tiles[t];
-                const float m0 = c.x - L.x, m1 = c.y - L.y, m2 = c.z - L.z;
-                const float mv = m0 * v.x + m1 * v.y + m2 * v.z;
-                const float d2 = (m0 * m0 + m1 * m1 + m2 * m2) - mv * mv;
-                const unsigned bits = __ballot_sync(FULL, valid && d2 <= c.w);
-                if (lane == 0) bitmap[t * LINE_WORDS + w] = bits;
+        __syncthreads();                                 // previous pass is done with rays / bitmap
+        for (int w = tid; w < n_tiles * LINE_WORDS; w += LINE_THREADS) bitmap[w] = 0u;
+        for (int k = tid; k < 2 * nr; k += LINE_THREADS) rays[k] = __ldg(lines + 2 * cur + k);
+        __syncthreads();
+        // ---- phase 1: conservative two-level culling, one ray per warp pass, lanes = (super-)tiles.
+        //      dist(centre, line)^2 <= (w + r + slack)^2 is necessary for any bin of the (super-)tile to be hit.
+        for (int r = warp; r < nr; r += NW) {
+            const float4 ra = rays[2 * r], rb = rays[2 * r + 1];
+            const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
+            const uint32_t rbit = 1u << (r & 31);
+            const int rword = r >> 5;
+            for (int s0 = 0; s0 < n_super; s0 += 32) {
+                const int sidx = s0 + lane;
+                bool pass = false;
+                if (sidx < n_super) {
+                    const float4 c = s_super[sidx];
+                    const float m0 = c.x - L.x, m1 = c.y - L.y, m2 = c.z - L.z;
+                    const float mv = m0 * v.x + m1 * v.y + m2 * v.z;
+                    pass = (m0 * m0 + m1 * m1 + m2 * m2) - mv * mv <= c.w;
+                }
+                unsigned sm_ = __ballot_sync(FULL, pass);
+                // two candidate super-tiles per round: lanes 0-15 take the first, 16-31 the second
+                while (sm_) {
+                    const int a0 = __ffs(sm_) - 1; sm_ &= sm_ - 1;
+                    int a1 = -1;
+                    if (sm_) { a1 = __ffs(sm_) - 1; sm_ &= sm_ - 1; }
+                    const int mine = lane < 16 ? a0 : a1;
+                    if (mine >= 0) {
+                        const uint32_t ij = s_sup_ij[s0 + mine];
+                        const int sub = lane & 15;
+                        const int ti = (int)(ij >> 16) + (sub >> 2), tj = (int)(ij & 0xffffu) + (sub & 3);
+                        if (ti < M.nt_theta && tj < M.nt_phi) {
+                            const int t = ti * M.nt_phi + tj;
+                            const float4 c = s_tiles[t];
+                            const float m0 = c.x - L.x, m1 = c.y - L.y, m2 = c.z - L.z;
+                            const float mv = m0 * v.x + m1 * v.y + m2 * v.z;
+                            if ((m0 * m0 + m1 * m1 + m2 * m2) - mv * mv <= c.w) atomicOr(&bitmap[t * LINE_WORDS + rword], rbit);
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
         // ---- phase 2: bin-stationary tests; lane <-> bin of the tile, register accumulation
+        int ti = warp / M.nt_phi, tj = warp % M.nt_phi;
         for (int t = warp; t < n_tiles; t += NW) {
-            const int ti = t / M.nt_phi, tj = t - ti * M.nt_phi;
-            const int i = ti * M.t_theta + lane / M.t_phi;
-            const int j = tj * M.t_phi + lane % M.t_phi;
+            const int i = ti * M.t_theta + li;
+            const int j = tj * M.t_phi + lj;
+            tj += NW;
+            while (tj >= M.nt_phi) { tj -= M.nt_phi; ti++; }
             const bool inb = (lane < M.t_theta * M.t_phi) && i < M.n_theta && j < M.n_phi;
             const int ii = inb ? i : 0, jj = inb ? j : 0;
             const float rs = t_rs[ii], pz = t_pz[ii], st = t_st[ii], ct = t_ct[ii], cp = t_cp[jj], sp = t_sp[jj];
             unsigned int acc = 0;
             for (int w = 0; w < nwords; w++) {
                 unsigned bits = bitmap[t * LINE_WORDS + w];
+                const float4* base = rays + w * 64;
                 while (bits) {
                     const int b = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    const float* p = rays + (w * 32 + b) * 6;
-                    const f3 L = {p[0], p[1], p[2]}, v = {p[3], p[4], p[5]};
+                    const float4 ra = base[2 * b], rb = base[2 * b + 1];
+                    const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
                     acc += line_hit(rs, pz, st, ct, cp, sp, M.w2, L, v) ? 1u : 0u;
                 }
             }
             if (inb && acc) atomicAdd(counts + (size_t)i * M.n_phi + j, (unsigned long long)acc);
         }
-        __syncthreads();
     }
 }
 
