@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1_000_000_000, help="rays per GPU per step (C3: 1e9)")
     ap.add_argument("--map", choices=["direction", "line"], default="direction")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--ref-rays", type=int, default=2_000_000, help="CPU sample size (rays)")
+    ap.add_argument("--ref-rays", type=int, default=20_000_000, help="CPU sample size (rays)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,6 +23,16 @@ def _scenes(mod):
         "thick_shell": dict(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=1.0, roughness=0.0,
                             max_bounces=10000),                                      # integratingSphereDetectorSweep.C:119
         "rough_half": dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000),
+        # edge cases of the domain
+        "suspended_limit_7": dict(theta_max=170.0, reflectance=1.0, max_bounces=7),          # every ray hits SetLimit
+        "limit_1": dict(theta_max=170.0, max_bounces=1),
+        "tiny_port_178": dict(theta_max=178.0, count_all_status=1),    # wall points below z=-100: absorbed rays pass the z test
+        "huge_port_100": dict(theta_max=100.0, roughness=0.0),
+        "black_wall": dict(theta_max=170.0, reflectance=0.0),          # every ray absorbed at its first hit
+        "all_specular_lobe": dict(theta_max=170.0, brdf_kind=1, brdf_param=(1.0, 1.0, 0.0, 0.0)),
+        "all_diffuse_lobe": dict(theta_max=170.0, brdf_kind=1, brdf_param=(0.3, 0.0, 1.0, 0.0), roughness=0.0),
+        "mirror_sphere": dict(theta_max=170.0, lambertian=0, roughness=0.0, reflectance=0.999, max_bounces=3000),
+        "small_world": dict(theta_max=165.0, world_half=102.0),
     }
 
 
@@ -40,13 +50,23 @@ def test_draws_bit_exact(ctx, oracle):
 
 
 @pytest.mark.parametrize("name", ["c2_lambert_rough", "c1_rho1_sigma0", "c3_custom_mirror", "specular",
-                                  "big_port_160", "thick_shell", "rough_half"])
+                                  "big_port_160", "thick_shell", "rough_half", "suspended_limit_7", "limit_1",
+                                  "tiny_port_178", "huge_port_100", "black_wall", "all_specular_lobe",
+                                  "all_diffuse_lobe", "mirror_sphere", "small_world"])
 def test_trace_records_bit_exact(ctx, oracle, altb, name):
     kw = _scenes(altb)[name]
     n = 100_000
     src = (-60.0, 0.0, -75.0) if "c1" not in name else (-60.0, 0.0, -80.0)
-    g_rec, g_st = ctx.trace_records(altb.scene(**kw), altb.source(src, (5.0, 0.0, 0.0)), n, seed=SEED)
-    o_rec, o_st = oracle.trace(oracle.scene(**kw), oracle.source(src, (5.0, 0.0, 0.0)), n, seed=SEED, prec=oracle.F32)
+    direction = (5.0, 0.0, 0.0) if "mirror" not in name else (5.0, 4.0, 1.0)       # (5,2,0),(5,4,0): fluxAtObserverOptimize.C:908-912
+    g_rec, g_st = ctx.trace_records(altb.scene(**kw), altb.source(src, direction), n, seed=SEED)
+    o_rec, o_st = oracle.trace(oracle.scene(**kw), oracle.source(src, direction), n, seed=SEED, prec=oracle.F32)
+    if name == "suspended_limit_7":
+        assert (g_rec["status"] != altb.ABSORBED).all() and (g_rec["status"] == altb.SUSPENDED).sum() > 0.8 * n
+        assert g_rec["n_hits"].max() == 7
+    if name == "black_wall":
+        assert (g_rec["status"] == altb.ABSORBED).all() and (g_rec["n_hits"] == 1).all()
+    if name == "tiny_port_178":
+        assert ((g_rec["status"] == altb.ABSORBED) & (g_rec["pos"][:, 2] < -100.0)).sum() > 0
     bad = np.flatnonzero((g_rec["status"] != o_rec["status"]) | (g_rec["n_hits"] != o_rec["n_hits"])
                          | (g_rec["pos"].view(np.uint32) != o_rec["pos"].view(np.uint32)).any(axis=1)
                          | (g_rec["dir"].view(np.uint32) != o_rec["dir"].view(np.uint32)).any(axis=1))
