@@ -122,6 +122,7 @@ def load_library():
     L.altb_replay.argtypes = [vp, P(Scene), vp, vp, vp, u64, P(MapSpec), vp, vp, vp]
     L.altb_map_records.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, vp]
     L.altb_draws.argtypes = [vp, u64, u64, u64, u32, vp]
+    L.altb_draws_lobe.argtypes = [vp, u64, u64, u64, u32, C.c_int, C.c_double, vp]
     L.altb_measure_fp32_peak.argtypes = [vp, P(C.c_double)]
     _lib = L
     return L
@@ -243,9 +244,9 @@ class Context:
         self._check(self._L.altb_map_records(self._h, C.byref(sc), C.byref(mp), _ptr(rec), len(rec), _ptr(counts)))
         return counts
 
-    def draws(self, seed, ray_id0, n, k):
+    def draws(self, seed, ray_id0, n, k, lobe_n=0, lobe_deg=0.0):
         out = np.zeros((n, 8), dtype=np.float32)
-        self._check(self._L.altb_draws(self._h, seed, ray_id0, n, k, _ptr(out)))
+        self._check(self._L.altb_draws_lobe(self._h, seed, ray_id0, n, k, lobe_n, lobe_deg, _ptr(out)))
         return out
 
     def measure_fp32_peak(self):

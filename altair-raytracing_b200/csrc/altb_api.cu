@@ -67,7 +67,13 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
         if (!(sum > 0)) return fail(ALTB_E_SCENE, "scene: brdf specular+diffuse must be > 0");
         ps = sc->brdf_param[1] / sum;
         bs = sc->brdf_param[0] * PI_D / 6.0;
+    } else if (sc->brdf_kind == 2) {
+        const double ne = sc->brdf_param[0];
+        if (!(ne >= 1.0 && ne <= 8.0) || ne != floor(ne)) return fail(ALTB_E_SCENE, "scene: cos^n lobe exponent must be an integer in 1..8");
+        if (!(sc->brdf_param[1] > 0.0 && sc->brdf_param[1] <= 90.0)) return fail(ALTB_E_SCENE, "scene: cos^n lobe max angle must be in (0,90] deg");
     } else if (sc->brdf_kind != 0) return fail(ALTB_E_SCENE, "scene: brdf_kind %d not supported", sc->brdf_kind);
+    k.lobe_n = sc->brdf_kind == 2 ? (int)sc->brdf_param[0] : 0;
+    k.lobe_ang = (float)(sc->brdf_kind == 2 ? sc->brdf_param[1] * PI_D / 180.0 : 0.0);
     k.rho = (float)sc->reflectance; k.sigma = (float)sc->roughness_rad;
     k.two_r1 = (float)(2.0 * g.R1); k.neg_inv_r1 = (float)(-1.0 / g.R1); k.nr_c = (float)(-0.5 / g.R1sq);
     k.zc = (float)g.zc; k.p_spec = (float)ps; k.brdf_s = (float)bs; k.exit_zf = (float)g.exit_z;
@@ -160,7 +166,7 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
     ts.P.kind0 = kind0;
     ts.P.keys = philox_expand(seed);
     ts.rough = sc->roughness_rad != 0.0;
-    ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : 0);
+    ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : (sc->brdf_kind == 2 ? 3 : 0));
     return 0;
 }
 
@@ -172,8 +178,8 @@ static void launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int*
 static int trace_blocks_per_sm(bool rough, int model) {
     int b = 0;
 #define OCC(R, M) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<R, M>, TRACE_THREADS, 0)
-    if (rough) { if (model == 0) OCC(true, 0); else if (model == 1) OCC(true, 1); else OCC(true, 2); }
-    else       { if (model == 0) OCC(false, 0); else if (model == 1) OCC(false, 1); else OCC(false, 2); }
+    if (rough) { if (model == 0) OCC(true, 0); else if (model == 1) OCC(true, 1); else if (model == 2) OCC(true, 2); else OCC(true, 3); }
+    else       { if (model == 0) OCC(false, 0); else if (model == 1) OCC(false, 1); else if (model == 2) OCC(false, 2); else OCC(false, 3); }
 #undef OCC
     return b > 0 ? b : 1;
 }
@@ -204,11 +210,13 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, uint64_t ray_id0,
     if (ts.rough) {
         if (ts.model == 0) launch_trace_t<true, 0>(P, d.rec, d.counter, blocks, st);
         else if (ts.model == 1) launch_trace_t<true, 1>(P, d.rec, d.counter, blocks, st);
-        else launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 2) launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
+        else launch_trace_t<true, 3>(P, d.rec, d.counter, blocks, st);
     } else {
         if (ts.model == 0) launch_trace_t<false, 0>(P, d.rec, d.counter, blocks, st);
         else if (ts.model == 1) launch_trace_t<false, 1>(P, d.rec, d.counter, blocks, st);
-        else launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 2) launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
+        else launch_trace_t<false, 3>(P, d.rec, d.counter, blocks, st);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -635,7 +643,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
     if (int rc = make_geom(scene, P.g, P.k)) return rc;
     P.n = (uint32_t)n_rays;
     const bool rough = scene->roughness_rad != 0.0;
-    const int model = !scene->lambertian ? 2 : (scene->brdf_kind == 1 ? 1 : 0);
+    const int model = !scene->lambertian ? 2 : (scene->brdf_kind == 1 ? 1 : (scene->brdf_kind == 2 ? 3 : 0));
     const uint64_t n_rec = tape_off[n_rays];
     if (int rc = ensure(d.rec, d.rec_cap, n_rays)) return rc;
     double* d_ray0 = nullptr; float* d_tape = nullptr; unsigned long long* d_off = nullptr; int* d_bin = nullptr;
@@ -654,11 +662,13 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
         if (rough) {
             if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
             else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else if (model == 2) launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else launch_replay_t<true, 3>(P, d_ray0, t4, d_off, d.rec, d.stream);
         } else {
             if (model == 0) launch_replay_t<false, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
             else if (model == 1) launch_replay_t<false, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else if (model == 2) launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            else launch_replay_t<false, 3>(P, d_ray0, t4, d_off, d.rec, d.stream);
         }
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: launch failed"); break; }
@@ -686,7 +696,11 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
 }
 
 // ---------------------------------------------------------------------------------- RNG probe
+extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, int lobe_n, double lobe_deg, float* out);
 extern "C" int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, float* out) {
+    return altb_draws_lobe(ctx, seed, ray_id0, n, k, 0, 0.0, out);
+}
+extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, int lobe_n, double lobe_deg, float* out) {
     if (!ctx || (!out && n)) return fail(ALTB_E_ARG, "altb_draws: NULL argument");
     if (n == 0) return 0;
     if (n > (1ull << 28)) return fail(ALTB_E_ARG, "altb_draws: n too large");
@@ -694,7 +708,7 @@ extern "C" int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64
     CK(cudaSetDevice(d.dev));
     float* buf = nullptr;
     CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
-    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), ray_id0, (uint32_t)n, k, buf);
+    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out, buf, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);

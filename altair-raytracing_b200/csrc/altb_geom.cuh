@@ -21,7 +21,7 @@ struct Geom {
     int lambertian, brdf_kind, max_bounces, count_all;
 };
 
-struct KConsts { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf; };
+struct KConsts { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n; };
 
 struct TraceParams {
     Geom g;

@@ -53,6 +53,8 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
     if (MODEL == 2) {
         float m = -2.0f * dot3(s.dir, n);
         d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
+    } else if (MODEL == 3) {
+        d = lobe_dir(n, dr.u_r, dr.u_phi, k.lobe_ang);
     } else if (MODEL == 1) {
         d = brdf_mix(n, s.dir, dr.u_sel < k.p_spec, dr.u_r, dr.g1, dr.u_phi, k.brdf_s);
     } else if (ROUGH) {
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const 
             if (alive) {
                 Draws dr;
                 make_draws<NEED_G>(P.keys, P.ray_id0 + idx, s.hits, dr);
+                if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + idx, s.hits, P.k.lobe_n, P.k.lobe_ang);
                 const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
                 else if (st) { store_record(rec, idx, s, st); alive = false; }
@@ -638,11 +641,13 @@ __global__ void __launch_bounds__(256) k_disk_hits(const altb_record* __restrict
 }
 
 // ------------------------------------------------------------------------------------ RNG probe
-__global__ void k_draws(const __grid_constant__ PhiloxKeys K, uint64_t ray_id0, uint32_t n, uint32_t k, float* __restrict__ out) {
+__global__ void k_draws(const __grid_constant__ PhiloxKeys K, uint64_t ray_id0, uint32_t n, uint32_t k, int lobe_n, float lobe_ang,
+                        float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Draws d;
     make_draws<true>(K, ray_id0 + i, k, d);
+    if (lobe_n > 0) d.u_r = lobe_accept(K, ray_id0 + i, k, lobe_n, lobe_ang);
     float4* o = reinterpret_cast<float4*>(out + 8 * (size_t)i);
     o[0] = make_float4(d.u_abs, d.u_r, d.u_phi, d.u_sel);
     o[1] = make_float4(d.u_psi, d.g0, d.g1, d.u_spare);

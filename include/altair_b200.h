@@ -51,10 +51,11 @@ typedef struct {
     int32_t lambertian;           /* EnableLambertian; 0 = specular mirror */
     int32_t max_bounces;          /* AOpticsManager::SetLimit */
     int32_t brdf_kind;            /* 0 Lambert; 1 "CustomMirror" = per-bounce spec/diffuse mixture of
-                                     nonLambertianFlux.C:147-208 */
+                                     nonLambertianFlux.C:147-208; 2 cos^n lobe of 'nonLambertianFlux copy.C':31-70 */
     int32_t count_all_status;     /* 0: only exited rays can pass the port test (batch macros);
                                      1: any final status (single-ray macros, makeIntegratingSphereNRays.C:74-78) */
-    double brdf_param[4];         /* kind 1: roughness, specular, diffuse (gBRDF(0.3,0.4,0.6)) */
+    double brdf_param[4];         /* kind 1: roughness, specular, diffuse (gBRDF(0.3,0.4,0.6));
+                                     kind 2: exponent (integer 1..8; reference 2), max angle [deg] (reference 60) */
     double exit_z;                /* exitPortZ, -100 cm */
 } altb_scene;
 
@@ -135,6 +136,8 @@ int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec
 
 /* Counter-based RNG exposed for verification: the 8 draws of hit k for rays ray_id0..+n-1. out[n][8]. */
 int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, float* out);
+/* same for brdf_kind 2, where slot [1] is the polar draw accepted by the cos^n rejection loop */
+int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, int lobe_n, double lobe_deg, float* out);
 
 /* FP32 FFMA-chain throughput of device 0 [TFLOP/s] (roofline denominator measured on the box). */
 int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops);

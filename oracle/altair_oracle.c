@@ -22,10 +22,11 @@
 typedef struct {
     double R1, R2, R1sq, R2sq, zc, T2, cth, sth, H, exit_z;
     int lambertian, brdf_kind, max_bounces, count_all;
+    int lobe_n;           /* brdf_kind 2: integer exponent of the cos^n lobe */
 } geom;
 
-typedef struct { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s; } consts_f;
-typedef struct { double rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s; } consts_d;
+typedef struct { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang; } consts_f;
+typedef struct { double rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang; } consts_d;
 
 static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
     if (!(sc->r_inner > 0) || !(sc->r_outer >= sc->r_inner) || !(sc->world_half > sc->r_outer)) return -1;
@@ -47,7 +48,14 @@ static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
         if (!(sum > 0)) return -1;
         ps = sc->brdf_param[1] / sum;
         bs = sc->brdf_param[0] * PI_D / 6.0;
+    } else if (sc->brdf_kind == 2) {   /* cos^n lobe of 'nonLambertianFlux copy.C':31-70: exponent, max angle [deg] */
+        double ne = sc->brdf_param[0];
+        if (!(ne >= 1.0 && ne <= 8.0) || ne != floor(ne)) return -1;
+        if (!(sc->brdf_param[1] > 0.0 && sc->brdf_param[1] <= 90.0)) return -1;
+        g->lobe_n = (int)ne;
     } else if (sc->brdf_kind != 0) return -1;
+    kd->lobe_ang = sc->brdf_kind == 2 ? sc->brdf_param[1] * PI_D / 180.0 : 0.0;
+    kf->lobe_ang = (float)kd->lobe_ang;
     kd->rho = sc->reflectance; kd->sigma = sc->roughness_rad;
     kd->two_r1 = 2.0 * g->R1; kd->neg_inv_r1 = -1.0 / g->R1; kd->nr_c = -0.5 / g->R1sq;
     kd->zc = g->zc; kd->p_spec = ps; kd->brdf_s = bs;
@@ -255,6 +263,29 @@ void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_P
     out[7] = 0.0f;
 }
 
+/* brdf_kind 2: the rejection loop of generateScatteredDirection ('nonLambertianFlux copy.C':47-69) only decides
+ * the polar angle (acceptance cos^n(theta) does not depend on phi), so it lives on the RNG side: slot [1] of the draw
+ * record becomes the ACCEPTED r1 (theta = max_angle * r1).  Attempts come from extra Philox blocks
+ * (counter word3 = 1, 2), four (r1, r3) pairs of 16 + 16 bits per block; after 8 rejections (p < 1e-4) the last r1 stands. */
+void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, float lobe_ang, float out[ORC_DRAWS_PER_HIT]) {
+    orc_draws(seed, ray_id, k, out);
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    float r1 = 0.0f;
+    for (uint32_t blk = 1; blk <= 2; blk++) {
+        uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, blk}, w[4];
+        orc_philox4x32_10(ctr, key, w);
+        for (int a = 0; a < 4; a++) {
+            r1 = (float)(w[a] >> 16) * 0x1p-16f;
+            float r3 = (float)(w[a] & 0xffffu) * 0x1p-16f;
+            float s, c, p = 1.0f;
+            orc_sincos_f32(lobe_ang * r1, &s, &c);
+            for (int e = 0; e < lobe_n; e++) p = p * c;
+            if (r3 <= p) { out[1] = r1; return; }
+        }
+    }
+    out[1] = r1;
+}
+
 /* ------------------------------------------------------------------ the two instantiations */
 #define REAL float
 #define SUF(n) n##_f
@@ -316,7 +347,8 @@ static void run_ray(const geom* g, const consts_f* kf, const consts_d* kd, int p
             if (ts && ts->tape) {
                 if (k >= ts->n_rec) { st = ORC_TAPE_END; break; }
                 memcpy(dr, ts->tape + 8 * (uint64_t)k, sizeof dr);
-            } else orc_draws(seed, ray_id, k, dr);
+            } else if (g->brdf_kind == 2) orc_draws_lobe(seed, ray_id, k, g->lobe_n, kf->lobe_ang, dr);
+            else orc_draws(seed, ray_id, k, dr);
             if (tape_out) memcpy(tape_out + 8 * (uint64_t)k, dr, sizeof dr);
             k++;
             st = bounce_f(g, kf, &s, dr);
@@ -337,7 +369,8 @@ static void run_ray(const geom* g, const consts_f* kf, const consts_d* kd, int p
             if (ts && ts->tape) {
                 if (k >= ts->n_rec) { st = ORC_TAPE_END; break; }
                 memcpy(dr, ts->tape + 8 * (uint64_t)k, sizeof dr);
-            } else orc_draws(seed, ray_id, k, dr);
+            } else if (g->brdf_kind == 2) orc_draws_lobe(seed, ray_id, k, g->lobe_n, kf->lobe_ang, dr);
+            else orc_draws(seed, ray_id, k, dr);
             k++;
             st = bounce_d(g, kd, &s, dr);
         }

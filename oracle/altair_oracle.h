@@ -53,10 +53,11 @@ typedef struct {
     double reflectance, roughness_rad;
     int32_t lambertian;   /* 1: diffuse model selected by brdf_kind; 0: ideal specular mirror */
     int32_t max_bounces;  /* AOpticsManager::SetLimit */
-    int32_t brdf_kind;    /* 0 Lambert, 1 spec/diffuse mixture (nonLambertianFlux.C:147-208) */
+    int32_t brdf_kind;    /* 0 Lambert, 1 spec/diffuse mixture (nonLambertianFlux.C:147-208),
+                             2 cos^n lobe ('nonLambertianFlux copy.C':31-70) */
     int32_t count_all_status; /* 0: only EXITED rays can "pass the port" (batch macros read
                                  GetExited/GetStopped only); 1: any status (single-ray macros) */
-    double brdf_param[4]; /* kind 1: roughness, specular, diffuse */
+    double brdf_param[4]; /* kind 1: roughness, specular, diffuse; kind 2: exponent (integer 1..8), max angle [deg] */
     double exit_z;
 } orc_scene;
 
@@ -92,6 +93,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* The 8 f32 draws for (seed, ray_id, hit index k) exactly as the CUDA kernels derive them. */
 void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]);
+/* brdf_kind 2: slot [1] is the polar draw ACCEPTED by the cos^n rejection loop ('nonLambertianFlux copy.C':47-69) */
+void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, float lobe_ang, float out[ORC_DRAWS_PER_HIT]);
 
 /* f32 math primitives of the arithmetic contract (exposed for unit tests). */
 void  orc_sincos2pi_f32(float u, float* s, float* c);

@@ -95,6 +95,7 @@ def lib():
     P = C.POINTER
     L.orc_philox4x32_10.argtypes = [P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]
     L.orc_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, P(C.c_float)]
+    L.orc_draws_lobe.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_float, P(C.c_float)]
     L.orc_sincos2pi_f32.argtypes = [C.c_float, P(C.c_float), P(C.c_float)]
     L.orc_sincos_f32.argtypes = [C.c_float, P(C.c_float), P(C.c_float)]
     L.orc_log_f32.argtypes = [C.c_float]

@@ -33,6 +33,9 @@ def _scenes(mod):
         "all_diffuse_lobe": dict(theta_max=170.0, brdf_kind=1, brdf_param=(0.3, 0.0, 1.0, 0.0), roughness=0.0),
         "mirror_sphere": dict(theta_max=170.0, lambertian=0, roughness=0.0, reflectance=0.999, max_bounces=3000),
         "small_world": dict(theta_max=165.0, world_half=102.0),
+        "cos2_lobe": dict(theta_max=170.0, brdf_kind=2, brdf_param=(2.0, 60.0, 0.0, 0.0)),     # 'nonLambertianFlux copy.C':31-70
+        "cos5_lobe_smooth": dict(theta_max=166.0, brdf_kind=2, brdf_param=(5.0, 45.0, 0.0, 0.0), roughness=0.0, reflectance=1.0,
+                                 max_bounces=10000),
     }
 
 
@@ -49,10 +52,23 @@ def test_draws_bit_exact(ctx, oracle):
         assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), f"k={k}"
 
 
+def test_lobe_draws_bit_exact(ctx, oracle):
+    import ctypes as C
+    g = ctx.draws(SEED, 77, 4096, 3, lobe_n=2, lobe_deg=60.0)
+    o = np.zeros((4096, 8), dtype=np.float32)
+    buf = (C.c_float * 8)()
+    for i in range(4096):
+        oracle.lib().orc_draws_lobe(SEED, 77 + i, 3, 2, np.float32(60.0 * np.pi / 180.0), buf)
+        o[i] = list(buf)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+    plain = ctx.draws(SEED, 77, 4096, 3)
+    assert np.array_equal(plain[:, [0, 2, 3, 4, 5, 6]], g[:, [0, 2, 3, 4, 5, 6]]) and not np.array_equal(plain[:, 1], g[:, 1])
+
+
 @pytest.mark.parametrize("name", ["c2_lambert_rough", "c1_rho1_sigma0", "c3_custom_mirror", "specular",
                                   "big_port_160", "thick_shell", "rough_half", "suspended_limit_7", "limit_1",
                                   "tiny_port_178", "huge_port_100", "black_wall", "all_specular_lobe",
-                                  "all_diffuse_lobe", "mirror_sphere", "small_world"])
+                                  "all_diffuse_lobe", "mirror_sphere", "small_world", "cos2_lobe", "cos5_lobe_smooth"])
 def test_trace_records_bit_exact(ctx, oracle, altb, name):
     kw = _scenes(altb)[name]
     n = 100_000
