@@ -384,10 +384,9 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    int per_sm = (int)((220 * 1024) / (ms.line_smem + 1024));
+    int per_sm = 1;    // persistent blocks: exactly the resident count (registers, shared memory, threads)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line, LINE_THREADS, ms.line_smem));
     if (per_sm < 1) per_sm = 1;
-    const int by_threads = 2048 / LINE_THREADS;
-    if (per_sm > by_threads) per_sm = by_threads;
     int blocks = d.sm_count * per_sm;
     const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
     if (blocks > need) blocks = need;

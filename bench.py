@@ -195,7 +195,10 @@ def run_ours(args):
     n_batches = -(-R // (1 << 26))
     achieved = FLOP_PER_BOUNCE * kst["n_bounces"] / kst["t_trace_s"] * 1e-12
     roofline = {"bound": "fp32", "kernel": "k_trace<rough,CustomMirror>", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE 2^26-ray launch of this kernel, from the
+                # `ncu --set full` capture in profiles/r01_ncu_final.md (algorithmic: 2^26 rays x 32 B = 2.147e9 B)
+                "traffic": 2.1186e9, "traffic_unit": "B per 2^26-ray launch (ncu, profiles/r01_ncu_final.md)",
                 "peak_source": "FFMA-chain probe measured live on this GPU (MEASURED_PEAKS.json has no FP32 number); "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "flop_per_bounce": FLOP_PER_BOUNCE, "launches": n_batches,
