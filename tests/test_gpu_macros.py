@@ -126,3 +126,36 @@ def test_cli_runner(M, altb):
     assert out.returncode == 0
     rows = _rows(os.path.join(M.out, "fluxmap_data.csv"))
     assert rows.shape == (900, 3) and rows[:, 2].sum() > 0 and open(os.path.join(M.out, "fluxmap_data.csv")).readline() == "theta,phi,fraction\n"
+
+
+def test_full_size_sweepDetector_against_reference_map(M, altb):
+    """BASELINE-size statistical parity on the GPU: the production macro (fluxAtObserverOptimize.C sweepDetector:
+    16 200 positions x 50 000 fresh rays = 8.1e8 rays; 12 524 s in the reference's own footer) against the reference's
+    committed map for the same parameters: per-bin Poisson z, chi2/ndf ~ 1, total hits."""
+    import json
+    import time
+    G = os.path.join(ROOT, "tests", "golden")
+    z = np.load(os.path.join(G, "perposition_170_dir5_0_0.npz"))
+    k_ref = z["hits"].astype(float)
+    t0 = time.time()
+    M.altbm_sweepDetector(0, b"full", -1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+    wall = time.time() - t0
+    path = M.altbm_last_csv().decode()
+    rows = _rows(path)
+    assert rows.shape == (16200, 3)
+    k = np.rint(rows[:, 2] * 50000)
+    n = 50000.0
+    p = (k + k_ref) / (2 * n)
+    ok = p * 2 * n > 30
+    zz = (k - k_ref)[ok] / np.sqrt(2 * n * p[ok] * (1 - p[ok]))
+    chi2 = (zz ** 2).mean()
+    text = open(path).read()
+    print(f"full-size sweepDetector: wall {wall:.2f} s, chi2/ndf {chi2:.3f}, max|z| {np.abs(zz).max():.2f}, "
+          f"hits {int(k.sum())} vs reference {int(k_ref.sum())}")
+    assert 0.8 < chi2 < 1.3, chi2
+    assert np.abs(zz).max() < 6.0
+    assert abs(k.sum() / k_ref.sum() - 1) < 0.025
+    assert "# Number of rays per position: 50000" in text and f"out of {16200 * 50000}" in text
+    assert wall < 120
+    json.dump({"wall_s": wall, "chi2_ndf": chi2, "max_abs_z": float(np.abs(zz).max()), "hits": int(k.sum()), "hits_reference": int(k_ref.sum()),
+               "reference_seconds": 12523.9}, open(os.path.join(ROOT, "gpurun_out", "full_size_sweepDetector.json"), "w"))
