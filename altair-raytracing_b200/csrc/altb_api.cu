@@ -658,6 +658,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
             rc = fail(ALTB_E_CUDA, "altb_replay: upload failed"); break;
         }
         const float4* t4 = reinterpret_cast<const float4*>(d_tape);
+        cudaEventRecord(d.ev[0], d.stream);
         if (rough) {
             if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
             else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
@@ -669,8 +670,16 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
             else if (model == 2) launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
             else launch_replay_t<false, 3>(P, d_ray0, t4, d_off, d.rec, d.stream);
         }
+        cudaEventRecord(d.ev[1], d.stream);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: launch failed"); break; }
+        if (getenv("ALTB_TIMING")) {       // replay is the one HBM-bound kernel (32 B of recorded draws per surface hit)
+            float ms = 0.f;
+            cudaEventSynchronize(d.ev[1]);
+            cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
+            fprintf(stderr, "[altb] k_replay: %llu rays, %llu tape records (%.3f GB), %.3f ms -> %.1f GB/s\n", (unsigned long long)n_rays,
+                    (unsigned long long)n_rec, n_rec * 32e-9, ms, n_rec * 32e-9 / (ms * 1e-3));
+        }
         std::vector<altb_record> tmp;
         altb_record* out = records;
         if (!out) { tmp.resize(n_rays); out = tmp.data(); }

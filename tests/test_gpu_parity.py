@@ -298,3 +298,19 @@ def test_full_size_properties(ctx, altb):
         parts += c
         tot += stp[0]["n_bounces"]
     assert np.array_equal(parts, c_all) and tot == s["n_bounces"]
+
+
+def test_in_process_multi_device_context(altb, ctx):
+    """altb_create(devices, n): one host thread drives several GPUs (what the C++ macros use); rays are split by
+    global id, the host adds the integer maps -> identical to the single-device result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs in one process (covered by the world_size-2 gloo test on CPU)")
+    n = 3_000_001
+    gm = altb.map_spec(mode=altb.MAP_LINE)
+    one, st1 = ctx.trace_fluxmap(altb.scene(), altb.source(), n, gm, seed=SEED)
+    with altb.Context(list(range(torch.cuda.device_count()))) as many:
+        cnt, stn = many.trace_fluxmap(altb.scene(), altb.source(), n, gm, seed=SEED)
+    assert np.array_equal(one, cnt)
+    for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+        assert st1[0][key] == stn[0][key]
