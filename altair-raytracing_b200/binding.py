@@ -123,6 +123,7 @@ def load_library():
     L.altb_map_records.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, vp]
     L.altb_draws.argtypes = [vp, u64, u64, u64, u32, vp]
     L.altb_draws_lobe.argtypes = [vp, u64, u64, u64, u32, C.c_int, C.c_double, vp]
+    L.altb_trace_paths.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, u32, vp, vp, vp]
     L.altb_measure_fp32_peak.argtypes = [vp, P(C.c_double)]
     _lib = L
     return L
@@ -253,3 +254,11 @@ class Context:
         v = C.c_double()
         self._check(self._L.altb_measure_fp32_peak(self._h, C.byref(v)))
         return v.value
+
+    def trace_paths(self, sc, src, n_rays, max_points, seed=4357, ray_id0=0):
+        """Polylines for small N: (points[n, max_points, 3] f32, n_points[n], status[n])."""
+        pts = np.zeros((n_rays, max_points, 3), dtype=np.float32)
+        npts = np.zeros(n_rays, dtype=np.uint32); status = np.zeros(n_rays, dtype=np.uint8)
+        self._check(self._L.altb_trace_paths(self._h, C.byref(sc), C.byref(src), ray_id0, n_rays, seed, max_points,
+                                             _ptr(pts), _ptr(npts), _ptr(status)))
+        return pts, npts, status

@@ -749,3 +749,45 @@ extern "C" int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops) {
     *tflops = best;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------- polylines (small N)
+#include "altb_paths.cuh"
+
+template <bool R, int M>
+static void launch_paths_t(const TraceParams& P, f3 sp, uint32_t mp, float* pts, uint32_t* np_, uint8_t* st, cudaStream_t s) {
+    k_trace_paths<R, M><<<(P.n + 127) / 128, 128, 0, s>>>(P, sp, mp, pts, np_, st);
+}
+
+extern "C" int altb_trace_paths(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0, uint64_t n_rays,
+                                uint64_t seed, uint32_t max_points, float* points, uint32_t* n_points, uint8_t* status) {
+    if (!ctx || !scene || !src || !points || !n_points || max_points < 2) return fail(ALTB_E_ARG, "altb_trace_paths: NULL/empty argument");
+    if (n_rays == 0) return 0;
+    if (n_rays * (uint64_t)max_points > (1ull << 30)) return fail(ALTB_E_ARG, "altb_trace_paths: n_rays * max_points too large (polylines are for small N)");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    TraceSetup ts;
+    if (int rc = setup_trace(scene, src, seed, ts)) return rc;
+    ts.P.ray_id0 = ray_id0; ts.P.n = (uint32_t)n_rays; ts.P.chunk = 0;
+    float* d_pts = nullptr; uint32_t* d_np = nullptr; uint8_t* d_st = nullptr;
+    const size_t nb = (size_t)n_rays * max_points * 3 * sizeof(float);
+    int rc = 0;
+    do {
+        if (cudaMalloc(&d_pts, nb) != cudaSuccess || cudaMalloc(&d_np, n_rays * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc(&d_st, n_rays) != cudaSuccess) { rc = fail(ALTB_E_NOMEM, "altb_trace_paths: cudaMalloc failed"); break; }
+        cudaMemsetAsync(d_pts, 0, nb, d.stream);
+        const f3 sp = {(float)src->pos[0], (float)src->pos[1], (float)src->pos[2]};
+        const bool R = ts.rough; const int M = ts.model;
+#define GO(RR, MM) launch_paths_t<RR, MM>(ts.P, sp, max_points, d_pts, d_np, d_st, d.stream)
+        if (R) { if (M == 0) GO(true, 0); else if (M == 1) GO(true, 1); else if (M == 2) GO(true, 2); else GO(true, 3); }
+        else   { if (M == 0) GO(false, 0); else if (M == 1) GO(false, 1); else if (M == 2) GO(false, 2); else GO(false, 3); }
+#undef GO
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_trace_paths: launch failed"); break; }
+        if (cudaMemcpyAsync(points, d_pts, nb, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess ||
+            cudaMemcpyAsync(n_points, d_np, n_rays * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream) != cudaSuccess ||
+            (status && cudaMemcpyAsync(status, d_st, n_rays, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) ||
+            cudaStreamSynchronize(d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_trace_paths: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(d_pts); cudaFree(d_np); cudaFree(d_st);
+    return rc;
+}

@@ -116,6 +116,12 @@ int altb_trace_exit_rays(altb_ctx* ctx, const altb_scene* scene, const altb_sour
 int altb_trace_records(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
                        uint64_t n_rays, uint64_t seed, altb_record* records, altb_stats* stats);
 
+/* Polylines for small N: what ARay::MakePolyLine3D feeds the reference's OpenGL views (makeIntegratingSphereNRays.C:69-72,
+ * makeIntegratingSphere1Ray.C:21-53).  points[n][max_points][3] (f32): point 0 = source, then every surface hit, then the
+ * world-box point of an exited ray; n_points[i] is the TRUE point count (= GetNpoints), only the first max_points are stored. */
+int altb_trace_paths(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0, uint64_t n_rays,
+                     uint64_t seed, uint32_t max_points, float* points, uint32_t* n_points, uint8_t* status);
+
 /* Physical thin-disk detectors, traced once and tested against all m poses.  Replaces the
  * per-position re-trace of integratingSphereDetectorSweep.C:31-105,134-172.
  * det_rot[m][9] row-major TGeoRotation matrices, det_center[m][3]. hits[m] is added to. */

@@ -778,3 +778,40 @@ int orc_disk_hits(const orc_scene* sc, const orc_record* rec, uint64_t n, const 
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ polylines (what ARay::MakePolyLine3D shows,
+ * makeIntegratingSphereNRays.C:69-72): point 0 = source, then every surface hit, then the world-box point of an
+ * exited ray.  F32 arithmetic (the kernels' mirror).  pts[n][max_points][3]; npts[i] is the TRUE number of points
+ * (1 + hits + exited), only the first max_points are stored. */
+int orc_trace_paths(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                    uint32_t max_points, float* pts, uint32_t* npts, uint8_t* status) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    double d0[3], x0[3];
+    int kind0 = launch(&g, src->pos, src->dir, d0, x0);
+    if (kind0 < 0) return -2;
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        float* p = pts + (size_t)i * max_points * 3;
+        uint32_t np_ = 0;
+        #define PUT(v) do { if (np_ < max_points) { p[3 * np_] = (v)[0]; p[3 * np_ + 1] = (v)[1]; p[3 * np_ + 2] = (v)[2]; } np_++; } while (0)
+        float s0[3] = {(float)src->pos[0], (float)src->pos[1], (float)src->pos[2]};
+        PUT(s0);
+        state_f s;
+        float dr[ORC_DRAWS_PER_HIT];
+        uint32_t k = 0;
+        int st = start_f(&g, &kf, &s, kind0, x0, d0);
+        while (!st) {
+            PUT(s.pos);
+            if (g.brdf_kind == 2) orc_draws_lobe(seed, ray_id0 + (uint64_t)i, k, g.lobe_n, kf.lobe_ang, dr);
+            else orc_draws(seed, ray_id0 + (uint64_t)i, k, dr);
+            k++;
+            st = bounce_f(&g, &kf, &s, dr);
+        }
+        if (st == ORC_EXITED) PUT(s.pos);
+        #undef PUT
+        npts[i] = np_;
+        if (status) status[i] = (uint8_t)st;
+    }
+    return 0;
+}

@@ -148,6 +148,11 @@ int orc_disk_hits(const orc_scene* sc, const orc_record* rec, uint64_t n, const 
                   const double* det_rot, uint32_t m, double det_r, double det_halfthick, uint64_t* hits);
 void orc_sweep_pose(double theta_deg, double phi_deg, double r, double center[3], double rot[9]);
 
+/* Polylines: point 0 = source, every surface hit, the world-box point of an exited ray (F32 arithmetic).
+ * pts[n][max_points][3]; npts[i] = true number of points, only the first max_points are stored. */
+int orc_trace_paths(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
+                    uint32_t max_points, float* pts, uint32_t* npts, uint8_t* status);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -118,6 +118,7 @@ def lib():
     L.orc_disk_hits.argtypes = [P(Scene), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                 C.c_double, C.c_void_p]
     L.orc_sweep_pose.argtypes = [C.c_double, C.c_double, C.c_double, P(C.c_double), P(C.c_double)]
+    L.orc_trace_paths.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_port_flag.argtypes = [P(Scene), C.c_void_p]
     L.orc_num_threads.restype = C.c_int
     _lib = L
@@ -227,3 +228,12 @@ def disk_hits(sc, rec, centers, rots, det_r=5.0, det_halfthick=0.1):
     if rc:
         raise RuntimeError(f"orc_disk_hits rc={rc}")
     return hits
+
+
+def trace_paths(sc, src, n, max_points, seed=4357, ray_id0=0):
+    pts = np.zeros((n, max_points, 3), dtype=np.float32)
+    npts = np.zeros(n, dtype=np.uint32); status = np.zeros(n, dtype=np.uint8)
+    rc = lib().orc_trace_paths(C.byref(sc), C.byref(src), ray_id0, n, seed, max_points, _ptr(pts), _ptr(npts), _ptr(status))
+    if rc:
+        raise RuntimeError(f"orc_trace_paths rc={rc}")
+    return pts, npts, status

@@ -314,3 +314,42 @@ def test_in_process_multi_device_context(altb, ctx):
     assert np.array_equal(one, cnt)
     for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
         assert st1[0][key] == stn[0][key]
+
+
+def test_map_stage_alone_on_host_records(ctx, oracle, altb):
+    """altb_map_records: the map stage on caller-provided records (what a host that already holds
+    GetExited()-style results would call), every map mode, ragged batch."""
+    sc_g, sc_o = altb.scene(theta_max=166.0), oracle.scene(theta_max=166.0)
+    rec, _ = oracle.trace(sc_o, oracle.source(), 25_003, seed=3, prec=oracle.F32)
+    ctx.set_batch(9_999)
+    try:
+        for mode in ("LINE", "TRACEONCE_COMPAT", "DIRECTION"):
+            g = ctx.map_records(sc_g, altb.map_spec(mode=getattr(altb, "MAP_" + mode)), rec)
+            o = oracle.map_records(sc_o, oracle.map_spec(mode=getattr(oracle, "MAP_" + mode)), rec, prec=oracle.F32)
+            assert np.array_equal(g, o), mode
+        gm = altb.map_spec(20, 10, 100.0, 40.0, altb.MAP_PER_POSITION, rays_per_position=125)
+        om = oracle.map_spec(20, 10, 100.0, 40.0, oracle.MAP_PER_POSITION, rays_per_position=125)
+        assert np.array_equal(ctx.map_records(sc_g, gm, rec), oracle.map_records(sc_o, om, rec, prec=oracle.F32))
+    finally:
+        ctx.set_batch(0)
+    assert ctx.map_records(sc_g, altb.map_spec(mode=altb.MAP_LINE), rec[:0]).sum() == 0
+
+
+def test_polylines_bit_exact(ctx, oracle, altb):
+    """altb_trace_paths: the per-ray hit-point polylines the reference draws with MakePolyLine3D
+    (makeIntegratingSphereNRays.C:69-72), small N."""
+    for kw, src in ((dict(theta_max=170.0), (-60.0, 0.0, -75.0)),
+                    (dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000), (-60.0, 0.0, -80.0))):
+        n, mp = 2000, 64
+        g_pts, g_np, g_st = ctx.trace_paths(altb.scene(**kw), altb.source(src), n, mp, seed=SEED)
+        o_pts, o_np, o_st = oracle.trace_paths(oracle.scene(**kw), oracle.source(src), n, mp, seed=SEED)
+        assert np.array_equal(g_np, o_np) and np.array_equal(g_st, o_st)
+        assert np.array_equal(g_pts.view(np.uint32), o_pts.view(np.uint32))
+        rec, _ = ctx.trace_records(altb.scene(**kw), altb.source(src), n, seed=SEED)
+        assert np.array_equal(g_np, 1 + rec["n_hits"] + (rec["status"] == altb.EXITED))      # = ARay::GetNpoints
+        assert np.allclose(g_pts[:, 0], np.float32(src)) and np.allclose(g_pts[:, 1], g_pts[0, 1])   # pencil beam: same first hit
+        short = g_np <= mp
+        last = g_pts[np.flatnonzero(short), g_np[short] - 1]
+        assert np.array_equal(last, rec["pos"][short])                                       # = GetLastPoint
+        r = np.linalg.norm(g_pts[:, 1].astype(np.float64), axis=1)
+        assert np.allclose(r, 100.1, atol=1e-4)                                              # hits lie on the inner sphere
