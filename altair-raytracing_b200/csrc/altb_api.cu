@@ -343,11 +343,8 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
     if (n == 0) return 0;
     const MapParams& M = ms.M;
     if (M.mode == ALTB_MAP_DIRECTION) {
-        static bool attr_done = false;
-        if (ms.dir_smem > 48 * 1024 && !attr_done) {
+        if (ms.dir_smem > 48 * 1024)      // per device: cheap enough to repeat
             CK(cudaFuncSetAttribute(k_map_direction, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_done = true;
-        }
         int blocks = d.sm_count * 2;
         const int need = (int)((n + 255) / 256);
         if (blocks > need) blocks = need;

@@ -159,3 +159,17 @@ def test_full_size_sweepDetector_against_reference_map(M, altb):
     assert wall < 120
     json.dump({"wall_s": wall, "chi2_ndf": chi2, "max_abs_z": float(np.abs(zz).max()), "hits": int(k.sum()), "hits_reference": int(k_ref.sum()),
                "reference_seconds": 12523.9}, open(os.path.join(ROOT, "gpurun_out", "full_size_sweepDetector.json"), "w"))
+
+
+def test_python_macro_wrapper(altb, oracle, tmp_path):
+    from altair_raytracing_b200 import macros
+    macros.set_output_dir(tmp_path)
+    macros.set("verbose", 0); macros.set("traceonce_rays", 5000)
+    macros.sweepDetectorTraceOnce(False, "py", 1, -60, 0, -75, 5, 0, 0, 170.0)
+    rows = _rows(macros.last_csv())
+    counts, _ = oracle.fluxmap(oracle.scene(), oracle.source(), 5000, oracle.map_spec(mode=oracle.MAP_TRACEONCE_COMPAT), prec=oracle.F32)
+    assert np.array_equal(np.rint(rows[:, 2] * 5000).astype(np.uint64), counts)
+    assert macros.last_fluxmap(1, 1) == counts[0] / 5000
+    macros.set("traceonce_rays", 100000)
+    with pytest.raises(KeyError):
+        macros.set("no_such_setting", 1)
