@@ -345,10 +345,12 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
     if (M.mode == ALTB_MAP_DIRECTION) {
         if (ms.dir_smem > 48 * 1024)      // per device: cheap enough to repeat
             CK(cudaFuncSetAttribute(k_map_direction, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        int blocks = d.sm_count * 2;
-        const int need = (int)((n + 255) / 256);
+        int per_sm = 1;    // the 64.8 kB histogram limits residency: more warps per block, grid = resident blocks
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_direction, DIR_THREADS, ms.dir_smem));
+        int blocks = d.sm_count * (per_sm < 1 ? 1 : per_sm);
+        const int need = (int)((n + DIR_THREADS - 1) / DIR_THREADS);
         if (blocks > need) blocks = need;
-        k_map_direction<<<blocks, 256, ms.dir_smem, st>>>(d.rec, n, M, d_counts, d_stats, d_bin);
+        k_map_direction<<<blocks, DIR_THREADS, ms.dir_smem, st>>>(d.rec, n, M, d_counts, d_stats, d_bin);
         ctx->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -686,7 +688,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
             rc = setup_map(d, scene, P.g, P.k, &m2, ms, d.stream);
             if (rc) break;
             MapParams M = ms.M; M.use_smem_hist = 0;
-            k_map_direction<<<d.sm_count * 2, 256, 0, d.stream>>>(d.rec, (uint32_t)n_rays, M, nullptr, nullptr, d_bin);
+            k_map_direction<<<d.sm_count * 2, DIR_THREADS, 0, d.stream>>>(d.rec, (uint32_t)n_rays, M, nullptr, nullptr, d_bin);
             ctx->launches++;
             if (cudaMemcpyAsync(bin, d_bin, n_rays * sizeof(int), cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "altb_replay: download failed"); break; }
         }

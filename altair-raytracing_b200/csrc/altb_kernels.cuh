@@ -352,7 +352,8 @@ __device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const f3& d
     return i * n_phi + j;
 }
 
-__global__ void __launch_bounds__(256) k_map_direction(const altb_record* __restrict__ rec, uint32_t n,
+static constexpr int DIR_THREADS = 512;
+__global__ void __launch_bounds__(DIR_THREADS) k_map_direction(const altb_record* __restrict__ rec, uint32_t n,
                                                        const MapParams M,
                                                        unsigned long long* __restrict__ counts,
                                                        unsigned long long* __restrict__ stats,
