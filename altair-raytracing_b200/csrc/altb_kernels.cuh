@@ -108,7 +108,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
 static constexpr int TRACE_THREADS = 256;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
-#define ALTB_BOUNCES_PER_CHECK 1
+#define ALTB_BOUNCES_PER_CHECK 2
 #endif
 static constexpr int QCAP = 32 + 32 * ALTB_BOUNCES_PER_CHECK;   // entries per queue per warp (pending + new per check)
 
