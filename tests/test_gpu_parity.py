@@ -353,3 +353,27 @@ def test_polylines_bit_exact(ctx, oracle, altb):
         assert np.array_equal(last, rec["pos"][short])                                       # = GetLastPoint
         r = np.linalg.norm(g_pts[:, 1].astype(np.float64), axis=1)
         assert np.allclose(r, 100.1, atol=1e-4)                                              # hits lie on the inner sphere
+
+
+@pytest.mark.parametrize("nt,npb,width", [(1, 1, 40.0), (7, 3, 40.0), (90, 45, 10.0), (181, 91, 40.0), (33, 2, 5.0), (2, 64, 60.0)])
+def test_line_map_odd_grids(ctx, oracle, altb, nt, npb, width):
+    """Tile / super-tile culling must stay conservative for any grid shape (partial tiles, single rows, odd sizes)."""
+    n = 12_000
+    for mode in ("LINE", "TRACEONCE_COMPAT"):
+        g, _ = ctx.trace_fluxmap(altb.scene(theta_max=168.0), altb.source(), n, altb.map_spec(nt, npb, 100.0, width, getattr(altb, "MAP_" + mode)), seed=5)
+        o, _ = oracle.fluxmap(oracle.scene(theta_max=168.0), oracle.source(), n, oracle.map_spec(nt, npb, 100.0, width, getattr(oracle, "MAP_" + mode)),
+                              seed=5, prec=oracle.F32)
+        assert np.array_equal(g[0], o), (mode, int(g.sum()), int(o.sum()))
+    d, _ = ctx.trace_fluxmap(altb.scene(theta_max=168.0), altb.source(), n, altb.map_spec(nt, npb, 100.0, width, altb.MAP_DIRECTION), seed=5)
+    od, _ = oracle.fluxmap(oracle.scene(theta_max=168.0), oracle.source(), n, oracle.map_spec(nt, npb, 100.0, width, oracle.MAP_DIRECTION), seed=5, prec=oracle.F32)
+    assert np.array_equal(d[0], od)
+
+
+def test_line_map_detector_geometry_variants(ctx, oracle, altb):
+    """Other detector radii / widths than the 100 cm / 40 cm of fluxAtObserverFast.C:1276-1277 (e.g. the 10 cm default
+    Detector() of fluxAtObserver.C / nonLambertianFlux.C)."""
+    n = 15_000
+    for radius, width in ((100.0, 10.0), (50.0, 40.0), (250.0, 80.0), (100.0, 199.0)):
+        g, _ = ctx.trace_fluxmap(altb.scene(), altb.source(), n, altb.map_spec(60, 30, radius, width, altb.MAP_LINE), seed=8)
+        o, _ = oracle.fluxmap(oracle.scene(), oracle.source(), n, oracle.map_spec(60, 30, radius, width, oracle.MAP_LINE), seed=8, prec=oracle.F32)
+        assert np.array_equal(g[0], o), (radius, width)
