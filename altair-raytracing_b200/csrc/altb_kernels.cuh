@@ -103,7 +103,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
 // turn out to hit the port edge (4 % of them) come back through the resume queue.
 #ifndef ALTB_TRACE_MINB
-#define ALTB_TRACE_MINB 3
+#define ALTB_TRACE_MINB 4
 #endif
 static constexpr int TRACE_THREADS = 256;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
