@@ -173,3 +173,41 @@ def test_python_macro_wrapper(altb, oracle, tmp_path):
     macros.set("traceonce_rays", 100000)
     with pytest.raises(KeyError):
         macros.set("no_such_setting", 1)
+
+
+def test_full_size_statistical_parity_other_goldens(M, ctx, altb):
+    """More of the reference's committed outputs at full size: the 163-degree production map (8 660 529 hits in its footer),
+    the trace-once maps as shipped (semantics B) at 1e7 rays, and the escape counts of all three port sizes at 1e8 rays."""
+    import json
+    G = os.path.join(ROOT, "tests", "golden")
+    gold = json.load(open(os.path.join(G, "golden.json")))
+    out = {}
+    # --- per-position, theta_max = 163
+    z = np.load(os.path.join(G, "perposition_163_dir5_0_0.npz"))
+    k_ref = z["hits"].astype(float)
+    M.altbm_sweepDetector(0, b"full163", -1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 163.0)
+    k = np.rint(_rows(M.altbm_last_csv().decode())[:, 2] * 50000)
+    n = 50000.0
+    p = (k + k_ref) / (2 * n)
+    ok = p * 2 * n > 30
+    zz = (k - k_ref)[ok] / np.sqrt(2 * n * p[ok] * (1 - p[ok]))
+    out["perposition_163"] = {"chi2_ndf": float((zz ** 2).mean()), "max_abs_z": float(np.abs(zz).max()), "hits": int(k.sum()),
+                              "hits_reference": int(k_ref.sum())}
+    assert 0.8 < out["perposition_163"]["chi2_ndf"] < 1.3 and np.abs(zz).max() < 6.0 and abs(k.sum() / k_ref.sum() - 1) < 0.025
+    # --- trace-once maps as shipped + escape fractions
+    for theta in (160, 164, 170):
+        zt = np.load(os.path.join(G, f"traceonce_{theta}.npz"))
+        kr, nr = zt["hits"].astype(float), float(zt["n_rays"])
+        n_big = 10_000_000
+        c, st = ctx.trace_fluxmap(altb.scene(theta_max=float(theta)), altb.source(), n_big, altb.map_spec(mode=altb.MAP_TRACEONCE_COMPAT), seed=1)
+        ratio = (c.sum() / n_big) / (kr.sum() / nr)
+        _, st8 = ctx.trace_fluxmap(altb.scene(theta_max=float(theta)), altb.source(), 100_000_000, altb.map_spec(mode=altb.MAP_DIRECTION), seed=2)
+        esc = st8[0]["n_exit_port"] / 1e8
+        ref = np.array(gold["escape_counts"][str(theta)], dtype=float)
+        esc_ref, esc_sig = ref.mean() / 1e5, ref.std(ddof=1) / 1e5 / np.sqrt(ref.size)
+        out[f"theta_{theta}"] = {"traceonce_sum_ratio": float(ratio), "escape_fraction": esc, "escape_fraction_reference": esc_ref,
+                                 "reference_sigma": esc_sig, "z": (esc - esc_ref) / esc_sig}
+        assert abs(ratio - 1) < 0.02
+        assert abs(esc - esc_ref) < 4 * esc_sig and abs(esc / esc_ref - 1) < 4e-3
+    print(json.dumps(out))
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "statistical_parity.json"), "w"), indent=1)
