@@ -12,11 +12,14 @@ ap.add_argument("--rays", type=int, default=8_000_000)
 ap.add_argument("--map", default="direction", choices=["direction", "line", "compat"])
 ap.add_argument("--brdf", type=int, default=1)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--rho", type=float, default=0.99)
+ap.add_argument("--theta", type=float, default=170.0)
+ap.add_argument("--limit", type=int, default=50000)
 a = ap.parse_args()
 mode = {"direction": A.MAP_DIRECTION, "line": A.MAP_LINE, "compat": A.MAP_TRACEONCE_COMPAT}[a.map]
 with A.Context([0]) as ctx:
     for r in range(a.reps):
-        counts, st = ctx.trace_fluxmap(A.scene(brdf_kind=a.brdf), A.source(), a.rays, A.map_spec(mode=mode), seed=4357,
+        counts, st = ctx.trace_fluxmap(A.scene(brdf_kind=a.brdf, reflectance=a.rho, theta_max=a.theta, max_bounces=a.limit), A.source(), a.rays, A.map_spec(mode=mode), seed=4357,
                                        ray_id0=r * a.rays)
         s = st[0]
         print(f"rep {r}: rays {s['n_rays']} bounces {s['n_bounces']} port {s['n_exit_port']} trace {s['t_trace_s']*1e3:.2f} ms "
