@@ -111,3 +111,28 @@ def test_disk_sweep_on_axis_fraction_is_plausible(oracle):
     hits = oracle.disk_hits(sc, rec, c[None, :], m[None, :], 5.0, 0.1)
     frac = hits[0] / n
     assert 0.6 * GOLD["detector_sweep_txt"]["theta0_mean_fraction"] < frac < 1.4 * GOLD["detector_sweep_txt"]["theta0_mean_fraction"], frac
+
+
+def test_nonlambertian_csv_is_the_plain_lambertian_map(oracle):
+    """flux_at_observer/fluxmap_data.csv (45x20, 10 cm detector, 100 000 rays per bin) is NOT what the committed
+    nonLambertianFlux.C would write (post-hoc BRDF re-scatter from the world box, roughness 0.5): it is reproduced by the
+    plain Lambertian trace of the same scene without roughness -- an older version of the macro wrote it (cf. the stale
+    ACLiC binary next to it).  So this golden pins the Lambert model with the 10 cm detector."""
+    z = np.load(os.path.join(G, "nonlambertian_45x20.npz"))
+    k_ref, n_ref = z["hits"].astype(float), float(z["rays_per_bin"])
+    n = 300_000
+    kw = dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000, count_all_status=1)
+    counts, _ = oracle.fluxmap(oracle.scene(**kw), oracle.source((-60, 0, -80), (5, 0, 0)), n,
+                               oracle.map_spec(45, 20, 100.0, 10.0, oracle.MAP_LINE), seed=3, prec=oracle.F64)
+    k = counts.astype(float)
+    assert abs((k.sum() / n) / (k_ref.sum() / n_ref) - 1) < 0.03
+    p = (k + k_ref) / (n + n_ref)
+    ok = p * (n + n_ref) > 30
+    zz = (k / n - k_ref / n_ref)[ok] / np.sqrt(p[ok] * (1 - p[ok]) * (1 / n + 1 / n_ref))
+    assert 0.75 < (zz ** 2).mean() < 1.35 and np.abs(zz).max() < 5.5
+    # the committed source's roughness 0.5 would be 8-12 % low on axis: excluded at > 5 sigma
+    kw["roughness"] = 0.5
+    c2, _ = oracle.fluxmap(oracle.scene(**kw), oracle.source((-60, 0, -80), (5, 0, 0)), n,
+                           oracle.map_spec(45, 20, 100.0, 10.0, oracle.MAP_LINE), seed=3, prec=oracle.F64)
+    on_axis = c2[:100].sum() / n / (k_ref[:100].sum() / n_ref)
+    assert on_axis < 0.95
