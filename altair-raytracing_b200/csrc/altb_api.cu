@@ -35,6 +35,7 @@ struct DevCtx {
     float* tables = nullptr; uint64_t tables_cap = 0;   // floats
     float4* tiles = nullptr; uint64_t tiles_cap = 0;
     float4* lines = nullptr; uint64_t lines_cap = 0;    // dense list of escaping rays for the line maps (2 float4 each)
+    float2* sincos = nullptr;                           // SC_N-entry azimuth table (altb_math.cuh: SinCosTab)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -51,6 +52,7 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     if (!(sc->theta_max_deg > 90.0) || !(sc->theta_max_deg < 180.0))
         return fail(ALTB_E_SCENE, "scene: theta_max_deg must be in (90,180)");
     if (sc->max_bounces < 1) return fail(ALTB_E_SCENE, "scene: max_bounces < 1");
+    if (!(sc->reflectance >= 0.0)) return fail(ALTB_E_SCENE, "scene: reflectance must be >= 0");
     const double th = sc->theta_max_deg * PI_D / 180.0;
     g.R1 = sc->r_inner; g.R2 = sc->r_outer;
     g.R1sq = g.R1 * g.R1; g.R2sq = g.R2 * g.R2;
@@ -77,6 +79,12 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     k.rho = (float)sc->reflectance; k.sigma = (float)sc->roughness_rad;
     k.two_r1 = (float)(2.0 * g.R1); k.neg_inv_r1 = (float)(-1.0 / g.R1); k.nr_c = (float)(-0.5 / g.R1sq);
     k.zc = (float)g.zc; k.p_spec = (float)ps; k.brdf_s = (float)bs; k.exit_zf = (float)g.exit_z;
+    // integer forms of the two comparisons (u_abs = k 2^-24, u_sel = k 2^-14 are exact in f32):
+    //   rho < u_abs   <=>  k > floor(rho 2^24)  <=>  w0 > (floor(rho 2^24) << 8 | 0xff)      (w0 = k << 8 | low byte)
+    //   u_sel < p     <=>  k < ceil(p 2^14)
+    const double fa = floor((double)k.rho * 16777216.0);
+    k.abs_thr = fa >= 16777216.0 ? 0xffffffffu : (((uint32_t)fa << 8) | 0xffu);
+    k.spec_thr = (uint32_t)ceil((double)k.p_spec * 16384.0);
     return 0;
 }
 
@@ -95,7 +103,7 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         if (d.dev < 0) continue;
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines);
+        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.sincos);
         for (auto& e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -124,13 +132,21 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
-            cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.sincos, SC_N * sizeof(float2)) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
             altb_destroy(ctx);
             return fail(ALTB_E_CUDA, "altb_create: device %d init failed: %s", dev, msg);
         }
         d.dev = dev;
         d.sm_count = prop.multiProcessorCount;
+        k_make_sincos_table<<<SC_N / 256, 256, 0, d.stream>>>(d.sincos);
+        ctx->launches++;
+        if (cudaStreamSynchronize(d.stream) != cudaSuccess) {
+            const char* msg = cudaGetErrorString(cudaGetLastError());
+            altb_destroy(ctx);
+            return fail(ALTB_E_CUDA, "altb_create: device %d: %s (is this an sm_100a GPU?)", dev, msg);
+        }
         for (auto& ev : d.ev) cudaEventCreate(&ev);
     }
     *out = ctx;
@@ -171,17 +187,17 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
 }
 
 template <bool R, int M>
-static void launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
-    k_trace<R, M><<<blocks, TRACE_THREADS, 0, st>>>(P, rec, counter);
-}
-
-static int trace_blocks_per_sm(bool rough, int model) {
-    int b = 0;
-#define OCC(R, M) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<R, M>, TRACE_THREADS, 0)
-    if (rough) { if (model == 0) OCC(true, 0); else if (model == 1) OCC(true, 1); else if (model == 2) OCC(true, 2); else OCC(true, 3); }
-    else       { if (model == 0) OCC(false, 0); else if (model == 1) OCC(false, 1); else if (model == 2) OCC(false, 2); else OCC(false, 3); }
-#undef OCC
-    return b > 0 ? b : 1;
+static cudaError_t launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
+    static thread_local int attr_dev = -1;      // the opt-in to >48 kB of dynamic shared memory is per device and per kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_trace<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_dev = dev;
+    }
+    k_trace<R, M><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
+    return cudaGetLastError();
 }
 
 // trace rays [ray_id0, ray_id0+n) into d.rec[0..n)
@@ -198,28 +214,29 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, uint64_t ray_id0,
     }
     TraceParams& P = ts.P;
     P.ray_id0 = ray_id0; P.n = n;
-    const int per_sm = trace_blocks_per_sm(ts.rough, ts.model);
-    int blocks = d.sm_count * per_sm;
+    P.sincos = d.sincos;
+    int blocks = d.sm_count;                           // persistent: one 1024-thread block per SM
     const uint32_t warps_needed = (n + 31) / 32;
-    if ((uint32_t)blocks * 8u > warps_needed) blocks = (int)((warps_needed + 7) / 8);
+    if ((uint32_t)blocks * TRACE_WARPS > warps_needed) blocks = (int)((warps_needed + TRACE_WARPS - 1) / TRACE_WARPS);
     // ids are claimed in chunks; small enough that the tail (last chunk per warp) stays short
     uint32_t chunk = 256;
-    while (chunk > 32 && (uint64_t)chunk * blocks * 8 * 4 > n) chunk >>= 1;
+    while (chunk > 32 && (uint64_t)chunk * blocks * TRACE_WARPS * 4 > n) chunk >>= 1;
     P.chunk = chunk;
     CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
+    cudaError_t le = cudaSuccess;
     if (ts.rough) {
-        if (ts.model == 0) launch_trace_t<true, 0>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 1) launch_trace_t<true, 1>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 2) launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
-        else launch_trace_t<true, 3>(P, d.rec, d.counter, blocks, st);
+        if (ts.model == 0) le = launch_trace_t<true, 0>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 1) le = launch_trace_t<true, 1>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 2) le = launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
+        else le = launch_trace_t<true, 3>(P, d.rec, d.counter, blocks, st);
     } else {
-        if (ts.model == 0) launch_trace_t<false, 0>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 1) launch_trace_t<false, 1>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 2) launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
-        else launch_trace_t<false, 3>(P, d.rec, d.counter, blocks, st);
+        if (ts.model == 0) le = launch_trace_t<false, 0>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 1) le = launch_trace_t<false, 1>(P, d.rec, d.counter, blocks, st);
+        else if (ts.model == 2) le = launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
+        else le = launch_trace_t<false, 3>(P, d.rec, d.counter, blocks, st);
     }
     ctx->launches++;
-    CK(cudaGetLastError());
+    CK(le);
     return 0;
 }
 
@@ -639,7 +656,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
     CK(cudaSetDevice(d.dev));
     ReplayParams P;
     if (int rc = make_geom(scene, P.g, P.k)) return rc;
-    P.n = (uint32_t)n_rays;
+    P.n = (uint32_t)n_rays; P.sincos = d.sincos;
     const bool rough = scene->roughness_rad != 0.0;
     const int model = !scene->lambertian ? 2 : (scene->brdf_kind == 1 ? 1 : (scene->brdf_kind == 2 ? 3 : 0));
     const uint64_t n_rec = tape_off[n_rays];
@@ -715,7 +732,7 @@ extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, u
     CK(cudaSetDevice(d.dev));
     float* buf = nullptr;
     CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
-    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
+    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out, buf, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
@@ -766,7 +783,7 @@ extern "C" int altb_trace_paths(altb_ctx* ctx, const altb_scene* scene, const al
     CK(cudaSetDevice(d.dev));
     TraceSetup ts;
     if (int rc = setup_trace(scene, src, seed, ts)) return rc;
-    ts.P.ray_id0 = ray_id0; ts.P.n = (uint32_t)n_rays; ts.P.chunk = 0;
+    ts.P.ray_id0 = ray_id0; ts.P.n = (uint32_t)n_rays; ts.P.chunk = 0; ts.P.sincos = d.sincos;
     float* d_pts = nullptr; uint32_t* d_np = nullptr; uint8_t* d_st = nullptr;
     const size_t nb = (size_t)n_rays * max_points * 3 * sizeof(float);
     int rc = 0;

@@ -21,7 +21,10 @@ struct Geom {
     int lambertian, brdf_kind, max_bounces, count_all;
 };
 
-struct KConsts { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n; };
+struct KConsts {
+    float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n;
+    uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
+};
 
 struct TraceParams {
     Geom g;
@@ -33,6 +36,7 @@ struct TraceParams {
     uint64_t ray_id0;     // global id of local ray 0
     uint32_t n;           // rays in this launch
     uint32_t chunk;       // ids a warp claims at a time
+    const float2* sincos; // device table, SC_N entries (altb_math.cuh: SinCosTab)
 };
 
 ALTB_HD void box_exit(const Geom& g, const double* x, const double* d, double* e) {

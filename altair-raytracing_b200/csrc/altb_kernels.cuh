@@ -36,7 +36,7 @@ static constexpr int ST_CROSSING = 100;
 // One surface hit.  Returns 0 to continue, a final ALTB_* status, or ST_CROSSING with
 // s.pos = the crossing point and s.dir = the new direction (DEFER_CROSSING only).
 template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
-__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayState& s, const Draws& dr) {
+__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, const SinCosTab& T, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
     if (s.where == EV_WALL) {
@@ -46,21 +46,21 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
         edge_normal(g, q, nn);
         nrm.x = (float)nn[0]; nrm.y = (float)nn[1]; nrm.z = (float)nn[2];
     }
-    if (k.rho < dr.u_abs) return ALTB_ABSORBED;
+    if (dr.absorb) return ALTB_ABSORBED;
     f3 n = nrm, t1, t2;
-    if (ROUGH) tilt_normal(nrm, dr.u_psi, dr.g0, k.sigma, n, t1, t2);
+    if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, n, t1, t2);
     f3 d;
     if (MODEL == 2) {
         float m = -2.0f * dot3(s.dir, n);
         d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
     } else if (MODEL == 3) {
-        d = lobe_dir(n, dr.u_r, dr.u_phi, k.lobe_ang);
+        d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
     } else if (MODEL == 1) {
-        d = brdf_mix(n, s.dir, dr.u_sel < k.p_spec, dr.u_r, dr.g1, dr.u_phi, k.brdf_s);
+        d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s);
     } else if (ROUGH) {
-        d = lambert_in(n, t1, t2, dr.u_r, dr.u_phi);
+        d = lambert_in(T, n, t1, t2, dr.u_r, dr.q_phi);
     } else {
-        d = lambert_dir(n, dr.u_r, dr.u_phi);
+        d = lambert_dir(T, n, dr.u_r, dr.q_phi);
     }
     float dn = dot3(d, nrm);
     if (dn < 0.0f) {
@@ -102,29 +102,38 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, RayS
 // every fifth iteration): the lane parks (crossing point, direction, id, hits) in the warp's shared-memory
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
 // turn out to hit the port edge (4 % of them) come back through the resume queue.
-#ifndef ALTB_TRACE_MINB
-#define ALTB_TRACE_MINB 4
-#endif
-static constexpr int TRACE_THREADS = 256;
+// One 1024-thread block per SM (64 registers per thread): its shared memory holds the 64 kB sin/cos table
+// (altb_math.cuh: SinCosTab) and the two queues of each of its 32 warps.
+static constexpr int TRACE_THREADS = 1024;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
 #define ALTB_BOUNCES_PER_CHECK 2
 #endif
-static constexpr int QCAP = 32 + 32 * ALTB_BOUNCES_PER_CHECK;   // entries per queue per warp (pending + new per check)
+// Queue bounds.  A lane that parks a crossing is dead until the next regeneration, so one pass of the loop adds at most
+// 32 crossings and the drain leaves fewer than 32 behind: nx <= 31 + 32.  Resumed rays are taken back before fresh ids
+// and every crossing frees a lane, so the resume queue holds at most the crossing backlog plus one pass: nr <= 63 + 32.
+static constexpr int XQCAP = 64, RQCAP = 96;
 
 struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
 
+static constexpr size_t TRACE_SMEM = SC_N * sizeof(float2) + (size_t)TRACE_WARPS * (XQCAP + RQCAP) * sizeof(QEntry);
+
 template <bool ROUGH, int MODEL>
-__global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const __grid_constant__ TraceParams P,
+__global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constant__ TraceParams P,
                                                          altb_record* __restrict__ rec,
                                                          unsigned int* __restrict__ counter) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
-    __shared__ QEntry s_xq[TRACE_WARPS][QCAP];      // crossings waiting for the slow path
-    __shared__ QEntry s_rq[TRACE_WARPS][QCAP];      // rays to resume (edge / wall events found by the slow path)
+    extern __shared__ __align__(16) unsigned char trace_smem[];
+    float2* s_tab = reinterpret_cast<float2*>(trace_smem);
+    QEntry* s_q = reinterpret_cast<QEntry*>(s_tab + SC_N);
+    for (int i = threadIdx.x; i < SC_N / 2; i += TRACE_THREADS)
+        reinterpret_cast<float4*>(s_tab)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
+    __syncthreads();
+    const SinCosTab T = {s_tab};
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    QEntry* xq = s_xq[warp];
-    QEntry* rq = s_rq[warp];
+    QEntry* xq = s_q + (size_t)warp * (XQCAP + RQCAP);   // crossings waiting for the slow path
+    QEntry* rq = xq + XQCAP;                              // rays to resume (edge / wall events found by the slow path)
     uint32_t nx = 0, nr = 0;          // warp-uniform queue fills
     uint32_t next = 0, end = 0;       // warp-uniform: ids [next,end) are claimed by this warp
     bool exhausted = false;           // warp-uniform: the global pool is empty
@@ -179,10 +188,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const 
         for (int rep = 0; rep < ALTB_BOUNCES_PER_CHECK; rep++) {
             bool crossing = false;
             if (alive) {
-                Draws dr;
-                make_draws<NEED_G>(P.keys, P.ray_id0 + idx, s.hits, dr);
+                HitDraws dr;
+                hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + idx, s.hits, dr);
                 if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + idx, s.hits, P.k.lobe_n, P.k.lobe_ang);
-                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, s, dr);
+                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, T, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
                 else if (st) { store_record(rec, idx, s, st); alive = false; }
             }
@@ -223,6 +232,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, ALTB_TRACE_MINB) k_trace(const 
             nx = base;
             const unsigned rm = __ballot_sync(FULL, resume);
             if (rm) {
+                if (nr + __popc(rm) > RQCAP) __trap();         // cannot happen (bounds above); never corrupt silently
                 if (resume) rq[nr + __popc(rm & lt_mask)] = e;
                 nr += __popc(rm);
             }
@@ -237,7 +247,7 @@ __global__ void k_fill_records(altb_record* rec, uint32_t n, altb_record proto) 
 }
 
 // ------------------------------------------------------------------------------------ K1r replay
-struct ReplayParams { Geom g; KConsts k; uint32_t n; };
+struct ReplayParams { Geom g; KConsts k; uint32_t n; const float2* sincos; };
 
 template <bool ROUGH, int MODEL>
 __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayParams P,
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
                                                 altb_record* __restrict__ rec) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    const SinCosTab T = {P.sincos};
     double d0[3], x0[3];
     const int kind0 = launch_ray(P.g, ray0 + 6 * (size_t)i, ray0 + 6 * (size_t)i + 3, d0, x0);
     RayState s;
@@ -269,7 +280,9 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         Draws dr;
         dr.u_abs = a.x; dr.u_r = a.y; dr.u_phi = a.z; dr.u_sel = a.w;
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, s, dr);
+        HitDraws h;
+        hit_from_draws(dr, P.k.rho, P.k.p_spec, h);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, s, h);
     }
     store_record(rec, i, s, st);
 }
@@ -641,13 +654,23 @@ __global__ void __launch_bounds__(256) k_disk_hits(const altb_record* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------ sin/cos table
+__global__ void k_make_sincos_table(float2* __restrict__ tab) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)SC_N) return;
+    float s, c;
+    sincos2pi((float)i * 0x1p-13f, s, c);
+    tab[i] = make_float2(s, c);
+}
+
 // ------------------------------------------------------------------------------------ RNG probe
-__global__ void k_draws(const __grid_constant__ PhiloxKeys K, uint64_t ray_id0, uint32_t n, uint32_t k, int lobe_n, float lobe_ang,
-                        float* __restrict__ out) {
+__global__ void k_draws(const __grid_constant__ PhiloxKeys K, const float2* __restrict__ sincos, uint64_t ray_id0, uint32_t n, uint32_t k,
+                        int lobe_n, float lobe_ang, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const SinCosTab T = {sincos};
     Draws d;
-    make_draws<true>(K, ray_id0 + i, k, d);
+    make_draws<true>(K, T, ray_id0 + i, k, d);
     if (lobe_n > 0) d.u_r = lobe_accept(K, ray_id0 + i, k, lobe_n, lobe_ang);
     float4* o = reinterpret_cast<float4*>(out + 8 * (size_t)i);
     o[0] = make_float4(d.u_abs, d.u_r, d.u_phi, d.u_sel);

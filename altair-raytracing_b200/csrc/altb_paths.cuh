@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(128) k_trace_paths(const __grid_constant__ Tra
     constexpr bool NEED_G = ROUGH || MODEL == 1;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    const SinCosTab T = {P.sincos};
     float* p = pts + (size_t)i * max_points * 3;
     uint32_t np_ = 0;
     auto put = [&](const f3& v) {
@@ -28,10 +29,10 @@ __global__ void __launch_bounds__(128) k_trace_paths(const __grid_constant__ Tra
     if (P.kind0 == EV_EXIT) st = ALTB_EXITED; else s.where = P.kind0;
     while (!st) {
         put(s.pos);
-        Draws dr;
-        make_draws<NEED_G>(P.keys, P.ray_id0 + i, s.hits, dr);
+        HitDraws dr;
+        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + i, s.hits, dr);
         if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + i, s.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, s, dr);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, s, dr);
     }
     if (st == ALTB_EXITED) put(s.pos);
     npts[i] = np_;

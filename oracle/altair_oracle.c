@@ -192,6 +192,25 @@ void orc_sincos2pi_f32(float u, float* s, float* c) {
     sincos_poly_f32(r * 6.2831855f, (int)q, s, c);
 }
 
+/* Azimuths are fixed-point turn fractions cut from the Philox block, so the kernels look their sin/cos up:
+ * tab[i] = orc_sincos2pi_f32(i / 8192) (8192 entries), and a 20-bit fraction q = hi:13 | lo:7 adds the second-order
+ * rotation by B = 2 pi lo / 2^20 (csrc/altb_math.cuh: SinCosTab).  The oracle restates exactly that. */
+static float g_sc_tab[8192][2];
+__attribute__((constructor)) static void sc_tab_init(void) {
+    for (int i = 0; i < 8192; i++) orc_sincos2pi_f32((float)i * 0x1p-13f, &g_sc_tab[i][0], &g_sc_tab[i][1]);
+}
+void orc_sincos2pi_q13(uint32_t q, float* s, float* c) { *s = g_sc_tab[q & 8191u][0]; *c = g_sc_tab[q & 8191u][1]; }
+void orc_sincos2pi_q20(uint32_t q, float* s, float* c) {
+    const float* a = g_sc_tab[(q >> 7) & 8191u];
+    float B = (float)(q & 127u) * (6.2831855f * 0x1p-20f);
+    float h = -0.5f * B;
+    *s = fmaf(fmaf(h, a[0], a[1]), B, a[0]);
+    *c = fmaf(fmaf(h, a[1], -a[0]), B, a[1]);
+}
+/* tape records carry the fractions as floats */
+static inline void sincos2pi_u13(float u, float* s, float* c) { orc_sincos2pi_q13((uint32_t)(u * 8192.0f), s, c); }
+static inline void sincos2pi_u20(float u, float* s, float* c) { orc_sincos2pi_q20((uint32_t)(u * 1048576.0f) & 0xfffffu, s, c); }
+
 void orc_sincos_f32(float x, float* s, float* c) {
     float q = rintf(x * 0.63661975f);
     float r = fmaf(q, -1.5707964f, x);
@@ -258,7 +277,7 @@ void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_P
     float u1 = (float)(t + 1u) * 0x1p-20f;                 /* (0,1] */
     float rad = sqrtf(-2.0f * orc_log_f32(u1));
     float s, c;
-    orc_sincos2pi_f32((float)((w[3] >> 6) & 0x1fffu) * 0x1p-13f, &s, &c);
+    orc_sincos2pi_q13((w[3] >> 6) & 0x1fffu, &s, &c);
     out[5] = rad * c; out[6] = rad * s;
     out[7] = 0.0f;
 }
@@ -294,7 +313,8 @@ void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, floa
 #define SQRT(x) sqrtf(x)
 #define FABS(x) fabsf(x)
 #define COPYSIGN(a, b) copysignf(a, b)
-#define SINCOS2PI(u, s, c) orc_sincos2pi_f32(u, s, c)
+#define SINCOS2PI_13(u, s, c) sincos2pi_u13(u, s, c)
+#define SINCOS2PI_20(u, s, c) sincos2pi_u20(u, s, c)
 #define SINCOS(x, s, c) orc_sincos_f32(x, s, c)
 #include "oracle_core.inc"
 #undef REAL
@@ -304,7 +324,8 @@ void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, floa
 #undef SQRT
 #undef FABS
 #undef COPYSIGN
-#undef SINCOS2PI
+#undef SINCOS2PI_13
+#undef SINCOS2PI_20
 #undef SINCOS
 
 #define REAL double
@@ -314,7 +335,8 @@ void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, floa
 #define SQRT(x) sqrt(x)
 #define FABS(x) fabs(x)
 #define COPYSIGN(a, b) copysign(a, b)
-#define SINCOS2PI(u, s, c) sincos2pi_d(u, s, c)
+#define SINCOS2PI_13(u, s, c) sincos2pi_d(u, s, c)
+#define SINCOS2PI_20(u, s, c) sincos2pi_d(u, s, c)
 #define SINCOS(x, s, c) sincos_d(x, s, c)
 #include "oracle_core.inc"
 #undef REAL
@@ -324,7 +346,8 @@ void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, floa
 #undef SQRT
 #undef FABS
 #undef COPYSIGN
-#undef SINCOS2PI
+#undef SINCOS2PI_13
+#undef SINCOS2PI_20
 #undef SINCOS
 
 /* ------------------------------------------------------------------ per-ray drivers */

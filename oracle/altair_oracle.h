@@ -98,6 +98,8 @@ void orc_draws_lobe(uint64_t seed, uint64_t ray_id, uint32_t k, int lobe_n, floa
 
 /* f32 math primitives of the arithmetic contract (exposed for unit tests). */
 void  orc_sincos2pi_f32(float u, float* s, float* c);
+void  orc_sincos2pi_q13(uint32_t q, float* s, float* c);   /* table form, 13-bit turn fraction */
+void  orc_sincos2pi_q20(uint32_t q, float* s, float* c);   /* table + second-order rotation, 20-bit turn fraction */
 void  orc_sincos_f32(float x, float* s, float* c);
 float orc_log_f32(float x);
 

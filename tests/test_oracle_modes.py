@@ -23,6 +23,18 @@ def test_f32_primitives_accuracy(oracle):
         x = 2 * np.pi * float(u)
         worst = max(worst, abs(s.value - np.sin(x)), abs(c.value - np.cos(x)))
     assert worst < 4e-7, worst
+    # table forms used for the RNG's fixed-point azimuths: 13-bit lookup, 20-bit lookup + second-order rotation
+    worst, norm = 0.0, 0.0
+    for q in np.concatenate([rng.integers(0, 1 << 20, 20000), [0, 127, 128, 1 << 18, (1 << 20) - 1]]):
+        L.orc_sincos2pi_q20(int(q), C.byref(s), C.byref(c))
+        x = 2 * np.pi * int(q) / (1 << 20)
+        worst = max(worst, abs(s.value - np.sin(x)), abs(c.value - np.cos(x)))
+        norm = max(norm, abs(s.value ** 2 + c.value ** 2 - 1.0))
+        if q % 128 == 0:
+            s2, c2 = C.c_float(), C.c_float()
+            L.orc_sincos2pi_q13(int(q) >> 7, C.byref(s2), C.byref(c2))
+            assert (s2.value, c2.value) == (s.value, c.value)
+    assert worst < 4e-7 and norm < 4e-7, (worst, norm)
     worst = 0.0
     for x in rng.uniform(-30, 30, 20000).astype(np.float32):
         L.orc_sincos_f32(float(x), C.byref(s), C.byref(c))
