@@ -85,6 +85,8 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     const double fa = floor((double)k.rho * 16777216.0);
     k.abs_thr = fa >= 16777216.0 ? 0xffffffffu : (((uint32_t)fa << 8) | 0xffu);
     k.spec_thr = (uint32_t)ceil((double)k.p_spec * 16384.0);
+    // Box-Muller radius of a 20-bit u1: |g| <= sqrt(2 * 20 ln 2) = 5.2655
+    k.tilt_small = fabs((double)k.sigma) * 5.2656 <= 0.78;
     return 0;
 }
 
@@ -180,6 +182,7 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
     const int kind0 = launch_ray(ts.P.g, src->pos, src->dir, ts.P.d0, ts.P.x0);
     if (kind0 < 0) return fail(ALTB_E_SOURCE, "source must lie strictly inside the inner sphere with a non-zero direction");
     ts.P.kind0 = kind0;
+    for (int i = 0; i < 3; i++) { ts.P.x0f[i] = (float)ts.P.x0[i]; ts.P.d0f[i] = (float)ts.P.d0[i]; }
     ts.P.keys = philox_expand(seed);
     ts.rough = sc->roughness_rad != 0.0;
     ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : (sc->brdf_kind == 2 ? 3 : 0));

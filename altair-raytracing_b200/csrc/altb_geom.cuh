@@ -23,6 +23,7 @@ struct Geom {
 
 struct KConsts {
     float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n;
+    int tilt_small;               // sigma * max|g| <= 0.78: the roughness tilt never needs the quadrant reduction
     uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
 };
 
@@ -32,6 +33,7 @@ struct TraceParams {
     int kind0;            // first event of the (identical) source rays
     double x0[3];         // its point
     double d0[3];         // unit source direction
+    float x0f[3], d0f[3]; // the same, rounded once (what every fresh ray starts from)
     PhiloxKeys keys;      // round keys of the seed
     uint64_t ray_id0;     // global id of local ray 0
     uint32_t n;           // rays in this launch

@@ -48,7 +48,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
     }
     if (dr.absorb) return ALTB_ABSORBED;
     f3 n = nrm, t1, t2;
-    if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, n, t1, t2);
+    if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n, t1, t2);
     f3 d;
     if (MODEL == 2) {
         float m = -2.0f * dot3(s.dir, n);
@@ -141,8 +141,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
     uint32_t idx = 0;
     RayState s;
     s.pos = {0.f, 0.f, 0.f}; s.dir = {0.f, 0.f, 0.f}; s.hits = 0; s.where = EV_WALL;
-    const f3 p_start = {(float)P.x0[0], (float)P.x0[1], (float)P.x0[2]};
-    const f3 d_start = {(float)P.d0[0], (float)P.d0[1], (float)P.d0[2]};
 
     while (true) {
         // ---- regeneration
@@ -174,7 +172,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     const uint32_t id = next + __popc(need & lt_mask);
                     if (id < end) {
                         alive = true; idx = id;
-                        s.pos = p_start; s.dir = d_start; s.hits = 0; s.where = P.kind0;
+                        s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
+                        s.hits = 0; s.where = P.kind0;
                     }
                 }
                 next = min(end, next + (uint32_t)__popc(need));

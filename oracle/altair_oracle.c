@@ -275,7 +275,7 @@ void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_P
     out[4] = (float)(w[3] >> 19) * 0x1p-13f;
     uint32_t t = ((w[0] & 0xffu) << 12) | ((w[1] & 0xffu) << 4) | (w[2] & 0xfu);
     float u1 = (float)(t + 1u) * 0x1p-20f;                 /* (0,1] */
-    float rad = sqrtf(-2.0f * orc_log_f32(u1));
+    float rad = sqrtf(2.0f * fabsf(orc_log_f32(u1)));   /* log <= 0; |.| keeps u1 = 1 at +0 */
     float s, c;
     orc_sincos2pi_q13((w[3] >> 6) & 0x1fffu, &s, &c);
     out[5] = rad * c; out[6] = rad * s;
