@@ -121,6 +121,7 @@ def load_library():
                                       vp, P(Stats)]
     L.altb_replay.argtypes = [vp, P(Scene), vp, vp, vp, u64, P(MapSpec), vp, vp, vp]
     L.altb_map_records.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, vp]
+    L.altb_probe_f32.argtypes = [vp, C.c_int, vp, u64, vp]
     L.altb_draws.argtypes = [vp, u64, u64, u64, u32, vp]
     L.altb_draws_lobe.argtypes = [vp, u64, u64, u64, u32, C.c_int, C.c_double, vp]
     L.altb_trace_paths.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, u32, vp, vp, vp]
@@ -249,6 +250,13 @@ class Context:
         out = np.zeros((n, 8), dtype=np.float32)
         self._check(self._L.altb_draws_lobe(self._h, seed, ray_id0, n, k, lobe_n, lobe_deg, _ptr(out)))
         return out
+
+    def probe_f32(self, op, x):
+        """y = op(x) with the kernels' f32 primitives (0 sqrt, 1 reciprocal, 2 log, 3/4 table sin/cos of 2 pi x / 2^20)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.zeros_like(x)
+        self._check(self._L.altb_probe_f32(self._h, op, _ptr(x), x.size, _ptr(y)))
+        return y
 
     def measure_fp32_peak(self):
         v = C.c_double()

@@ -199,6 +199,10 @@ static cudaError_t launch_trace_t(const TraceParams& P, altb_record* rec, unsign
         if (e != cudaSuccess) return e;
         attr_dev = dev;
     }
+    if (P.kind0 != EV_WALL) {   // source aimed at the port rim: generic tracer (k_trace's fresh rays start on the sphere)
+        k_trace_generic<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, rec);
+        return cudaGetLastError();
+    }
     k_trace<R, M><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
     return cudaGetLastError();
 }
@@ -741,6 +745,31 @@ extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, u
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     cudaFree(buf);
     if (e != cudaSuccess) return fail(ALTB_E_CUDA, "altb_draws: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- math probe
+extern "C" int altb_probe_f32(altb_ctx* ctx, int op, const float* x, uint64_t n, float* y) {
+    if (!ctx || ((!x || !y) && n)) return fail(ALTB_E_ARG, "altb_probe_f32: NULL argument");
+    if (op < 0 || op > 4) return fail(ALTB_E_ARG, "altb_probe_f32: op %d", op);
+    if (n == 0) return 0;
+    if (n > (1ull << 30)) return fail(ALTB_E_ARG, "altb_probe_f32: n too large");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    float *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc(&dx, n * sizeof(float)) != cudaSuccess || cudaMalloc(&dy, n * sizeof(float)) != cudaSuccess) {
+        cudaFree(dx);
+        return fail(ALTB_E_NOMEM, "altb_probe_f32: cudaMalloc failed");
+    }
+    cudaError_t e = cudaMemcpyAsync(dx, x, n * sizeof(float), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+        k_probe_f32<<<d.sm_count * 8, 256, 0, d.stream>>>(op, d.sincos, dx, (uint32_t)n, dy);
+        ctx->launches++;
+        e = cudaMemcpyAsync(y, dy, n * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(dx); cudaFree(dy);
+    if (e != cudaSuccess) return fail(ALTB_E_CUDA, "altb_probe_f32: %s", cudaGetErrorString(e));
     return 0;
 }
 

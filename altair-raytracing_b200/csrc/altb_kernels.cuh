@@ -35,11 +35,13 @@ static constexpr int ST_CROSSING = 100;
 
 // One surface hit.  Returns 0 to continue, a final ALTB_* status, or ST_CROSSING with
 // s.pos = the crossing point and s.dir = the new direction (DEFER_CROSSING only).
+// DEFER_CROSSING is the hot loop of k_trace: the ray is on the inner sphere by construction (s.where is not looked at),
+// everything that involves the port edge happens in the kernel's slow path.
 template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
 __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, const SinCosTab& T, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
-    if (s.where == EV_WALL) {
+    if (DEFER_CROSSING || s.where == EV_WALL) {
         nrm.x = s.pos.x * k.neg_inv_r1; nrm.y = s.pos.y * k.neg_inv_r1; nrm.z = s.pos.z * k.neg_inv_r1;
     } else {
         double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z}, nn[3];
@@ -71,7 +73,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
     if (s.hits >= (uint32_t)g.max_bounces) { s.dir = d; return ALTB_SUSPENDED; }
     int kind;
     double out[3];
-    if (s.where == EV_WALL) {
+    if (DEFER_CROSSING || s.where == EV_WALL) {
         float t = k.two_r1 * dn;
         f3 x = {fma_(t, d.x, s.pos.x), fma_(t, d.y, s.pos.y), fma_(t, d.z, s.pos.z)};
         float sc = fma_(dot3(x, x), k.nr_c, 1.5f);
@@ -109,10 +111,29 @@ static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
 #define ALTB_BOUNCES_PER_CHECK 2
 #endif
+#ifndef ALTB_BPC_UNROLL
+#define ALTB_BPC_UNROLL 1
+#endif
 // Queue bounds.  A lane that parks a crossing is dead until the next regeneration, so one pass of the loop adds at most
 // 32 crossings and the drain leaves fewer than 32 behind: nx <= 31 + 32.  Resumed rays are taken back before fresh ids
 // and every crossing frees a lane, so the resume queue holds at most the crossing backlog plus one pass: nr <= 63 + 32.
 static constexpr int XQCAP = 64, RQCAP = 96;
+
+// A ray on the port edge: bounce with the generic step until it is back on the inner sphere (returns 0) or ends
+// (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
+// loop any registers.
+template <bool ROUGH, int MODEL>
+__device__ __noinline__ int edge_bounces(const TraceParams& P, const SinCosTab& T, uint32_t id, RayState& t) {
+    constexpr bool NEED_G = ROUGH || MODEL == 1;
+    int st;
+    do {
+        HitDraws dr;
+        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + id, t.hits, dr);
+        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + id, t.hits, P.k.lobe_n, P.k.lobe_ang);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, t, dr);
+    } while (st == 0 && t.where != EV_WALL);
+    return st;
+}
 
 struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
 
@@ -152,8 +173,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     const QEntry e = rq[nr - 1 - rank];
                     s.pos = {e.a.x, e.a.y, e.a.z}; s.dir = {e.a.w, e.b.x, e.b.y};
                     idx = __float_as_uint(e.b.z);
-                    const uint32_t hw = __float_as_uint(e.b.w);
-                    s.hits = hw & 0x7fffffffu; s.where = (hw >> 31) ? EV_EDGE : EV_WALL;
+                    s.hits = __float_as_uint(e.b.w);
                     alive = true;
                 }
                 nr -= min(nr, (uint32_t)__popc(need));
@@ -173,7 +193,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     if (id < end) {
                         alive = true; idx = id;
                         s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
-                        s.hits = 0; s.where = P.kind0;
+                        s.hits = 0;
                     }
                 }
                 next = min(end, next + (uint32_t)__popc(need));
@@ -183,7 +203,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         if (!any_alive && exhausted && nx == 0 && nr == 0) break;
 
         // ---- ALTB_BOUNCES_PER_CHECK surface hits per live lane between two regeneration checks
+#if ALTB_BPC_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
         for (int rep = 0; rep < ALTB_BOUNCES_PER_CHECK; rep++) {
             bool crossing = false;
             if (alive) {
@@ -224,8 +248,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     p[0] = e.a;
                     p[1] = make_float4(e.b.x, e.b.y, e.b.w, __uint_as_float((uint32_t)ALTB_EXITED));
                 } else {
-                    resume = true;
-                    if (kind == EV_EDGE) e.b.w = __uint_as_float(__float_as_uint(e.b.w) | 0x80000000u);
+                    // Port-edge hit (4 % of the crossings, 3e-4 of the surface hits): bounce on the edge right here, with the
+                    // generic step, until the ray is back on the inner sphere (resume) or ends.  Few lanes, rare.
+                    const uint32_t id = __float_as_uint(e.b.z);
+                    RayState t;
+                    t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
+                    t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
+                    const int st = edge_bounces<ROUGH, MODEL>(P, T, id, t);
+                    if (st) store_record(rec, id, t, st);
+                    else {
+                        resume = true;
+                        e.a = make_float4(t.pos.x, t.pos.y, t.pos.z, t.dir.x);
+                        e.b = make_float4(t.dir.y, t.dir.z, e.b.z, __uint_as_float(t.hits));
+                    }
                 }
             }
             nx = base;
@@ -238,6 +273,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             __syncwarp();
         }
     }
+}
+
+// Generic one-thread-per-ray tracer with the in-line step: used when the source's first event is the port edge itself
+// (k_trace's fresh rays must start on the inner sphere), i.e. for sources aimed exactly at the rim.
+template <bool ROUGH, int MODEL>
+__global__ void __launch_bounds__(128) k_trace_generic(const __grid_constant__ TraceParams P, altb_record* __restrict__ rec) {
+    constexpr bool NEED_G = ROUGH || MODEL == 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const SinCosTab T = {P.sincos};
+    RayState s;
+    s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
+    s.hits = 0; s.where = P.kind0;
+    int st = 0;
+    while (!st) {
+        HitDraws dr;
+        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + i, s.hits, dr);
+        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + i, s.hits, P.k.lobe_n, P.k.lobe_ang);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, s, dr);
+    }
+    store_record(rec, i, s, st);
 }
 
 // every source ray leaves through the port without touching anything
@@ -674,6 +730,20 @@ __global__ void k_draws(const __grid_constant__ PhiloxKeys K, const float2* __re
     float4* o = reinterpret_cast<float4*>(out + 8 * (size_t)i);
     o[0] = make_float4(d.u_abs, d.u_r, d.u_phi, d.u_sel);
     o[1] = make_float4(d.u_psi, d.g0, d.g1, d.u_spare);
+}
+
+// ------------------------------------------------------------------------------------ math probe
+__global__ void k_probe_f32(int op, const float2* __restrict__ sincos, const float* __restrict__ x, uint32_t n, float* __restrict__ y) {
+    const SinCosTab T = {sincos};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = x[i];
+        float s = 0.f, c = 0.f, r;
+        if (op == 0) r = sqrt_c(v);
+        else if (op == 1) r = rcp_c(v);
+        else if (op == 2) r = log_f32(v);
+        else { T.at20((uint32_t)v & 0xfffffu, s, c); r = op == 3 ? s : c; }
+        y[i] = r;
+    }
 }
 
 // ------------------------------------------------------------------------------------ FP32 peak probe

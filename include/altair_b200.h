@@ -145,6 +145,11 @@ int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint3
 /* same for brdf_kind 2, where slot [1] is the polar draw accepted by the cos^n rejection loop */
 int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, int lobe_n, double lobe_deg, float* out);
 
+/* f32 primitives of the arithmetic contract exposed for verification: y[i] = op(x[i]) on device 0.
+ * op 0: sqrt (written-out IEEE fast path), 1: reciprocal (same), 2: natural log polynomial,
+ * 3/4: sin/cos of 2 pi q / 2^20 from the azimuth table, q = (uint32) x[i]. */
+int altb_probe_f32(altb_ctx* ctx, int op, const float* x, uint64_t n, float* y);
+
 /* FP32 FFMA-chain throughput of device 0 [TFLOP/s] (roofline denominator measured on the box). */
 int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops);
 

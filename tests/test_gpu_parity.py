@@ -52,6 +52,36 @@ def test_draws_bit_exact(ctx, oracle):
         assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), f"k={k}"
 
 
+def test_f32_primitives_are_ieee_exact(ctx, oracle):
+    """The written-out sqrt / reciprocal fast paths must be THE correctly rounded results (what sqrtf and 1.0f/x give on
+    the CPU) on every argument the kernels can feed them: exhaustive over the 2^24 + 1 uniforms k 2^-24 (sqrt(u_r),
+    sqrt(1 - u_r)), over every f32 in [1, 2] (orthonormal-basis reciprocal) and dense samples of the other ranges; the
+    log polynomial and the azimuth table must equal the oracle's restatement bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    u = (np.arange((1 << 24) + 1, dtype=np.float64) * 2.0 ** -24).astype(np.float32)
+    assert np.array_equal(ctx.probe_f32(0, u).view(np.uint32), np.sqrt(u).view(np.uint32))
+    x = np.concatenate([rng.uniform(0.25, 4.0, 4_000_000), 10.0 ** rng.uniform(-6.5, 1.5, 4_000_000)]).astype(np.float32)
+    assert np.array_equal(ctx.probe_f32(0, x).view(np.uint32), np.sqrt(x).view(np.uint32))
+    m = (np.arange((1 << 23) + 1, dtype=np.uint32) + np.uint32(0x3f800000)).view(np.float32)      # every f32 in [1, 2]
+    for v in (m, -m, rng.uniform(0.4, 2.5, 4_000_000).astype(np.float32)):
+        assert np.array_equal(ctx.probe_f32(1, v).view(np.uint32), (np.float32(1.0) / v).view(np.uint32))
+    L = oracle.lib()
+    L.orc_log_f32.restype = C.c_float
+    t = rng.integers(1, (1 << 20) + 1, 60000)
+    u1 = (t.astype(np.float64) * 2.0 ** -20).astype(np.float32)
+    want = np.array([L.orc_log_f32(C.c_float(float(v))) for v in u1], dtype=np.float32)
+    assert np.array_equal(ctx.probe_f32(2, u1).view(np.uint32), want.view(np.uint32))
+    q = np.concatenate([rng.integers(0, 1 << 20, 60000), np.arange(0, 1 << 20, 128)[:2000], [0, 127, (1 << 20) - 1]]).astype(np.uint32)
+    s_, c_ = C.c_float(), C.c_float()
+    ws, wc = np.zeros(q.size, np.float32), np.zeros(q.size, np.float32)
+    for i, v in enumerate(q):
+        L.orc_sincos2pi_q20(int(v), C.byref(s_), C.byref(c_))
+        ws[i], wc[i] = s_.value, c_.value
+    assert np.array_equal(ctx.probe_f32(3, q.astype(np.float32)).view(np.uint32), ws.view(np.uint32))
+    assert np.array_equal(ctx.probe_f32(4, q.astype(np.float32)).view(np.uint32), wc.view(np.uint32))
+
+
 def test_lobe_draws_bit_exact(ctx, oracle):
     import ctypes as C
     g = ctx.draws(SEED, 77, 4096, 3, lobe_n=2, lobe_deg=60.0)
