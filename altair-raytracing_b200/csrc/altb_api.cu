@@ -86,8 +86,20 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     k.abs_thr = fa >= 16777216.0 ? 0xffffffffu : (((uint32_t)fa << 8) | 0xffu);
     k.spec_thr = (uint32_t)ceil((double)k.p_spec * 16384.0);
     // Box-Muller radius of a 20-bit u1: |g| <= sqrt(2 * 20 ln 2) = 5.2655
-    k.tilt_small = fabs((double)k.sigma) * 5.2656 <= 0.78;
+    k.tilt_small = fabs((double)k.sigma) * 5.2656 <= (double)SINCOS_DIRECT_MAX;
+    k.spec_small = fabs((double)k.brdf_s) * 5.2656 <= (double)SINCOS_DIRECT_MAX;
     return 0;
+}
+
+// log table of DrawTabs::log_u20 (altb_math.cuh): double precision, rounded once
+static std::vector<float4> make_log_table() {
+    std::vector<float4> t(LG_N);
+    for (int hi = 0; hi < LG_N; hi++) {
+        const double mh = 1.0 + hi / 128.0;
+        const bool half = hi >= 53;                                 // m_hi > ~sqrt(2): measure from the next power of two
+        t[hi] = make_float4((float)log(half ? mh * 0.5 : mh), (float)(1.0 / mh), half ? -146.0f : -147.0f, 0.0f);
+    }
+    return t;
 }
 
 // ---------------------------------------------------------------------------------- context
@@ -135,7 +147,7 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMalloc(&d.sincos, SC_N * sizeof(float2)) != cudaSuccess) {
+            cudaMalloc(&d.sincos, TABS_BYTES) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
             altb_destroy(ctx);
             return fail(ALTB_E_CUDA, "altb_create: device %d init failed: %s", dev, msg);
@@ -144,7 +156,9 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         d.sm_count = prop.multiProcessorCount;
         k_make_sincos_table<<<SC_N / 256, 256, 0, d.stream>>>(d.sincos);
         ctx->launches++;
-        if (cudaStreamSynchronize(d.stream) != cudaSuccess) {
+        const std::vector<float4> lg = make_log_table();
+        if (cudaMemcpyAsync(d.sincos + SC_N, lg.data(), LG_N * sizeof(float4), cudaMemcpyHostToDevice, d.stream) != cudaSuccess ||
+            cudaStreamSynchronize(d.stream) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
             altb_destroy(ctx);
             return fail(ALTB_E_CUDA, "altb_create: device %d: %s (is this an sm_100a GPU?)", dev, msg);

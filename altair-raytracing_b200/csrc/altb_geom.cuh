@@ -23,7 +23,7 @@ struct Geom {
 
 struct KConsts {
     float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n;
-    int tilt_small;               // sigma * max|g| <= 0.78: the roughness tilt never needs the quadrant reduction
+    int tilt_small, spec_small;   // sigma * max|g| <= 0.9 / brdf_s * max|g| <= 0.9: sin/cos without the quadrant reduction
     uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
 };
 
@@ -38,7 +38,7 @@ struct TraceParams {
     uint64_t ray_id0;     // global id of local ray 0
     uint32_t n;           // rays in this launch
     uint32_t chunk;       // ids a warp claims at a time
-    const float2* sincos; // device table, SC_N entries (altb_math.cuh: SinCosTab)
+    const float2* sincos; // device tables: SC_N sin/cos entries + LG_N log entries (altb_math.cuh: DrawTabs)
 };
 
 ALTB_HD void box_exit(const Geom& g, const double* x, const double* d, double* e) {

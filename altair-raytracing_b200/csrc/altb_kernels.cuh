@@ -38,7 +38,7 @@ static constexpr int ST_CROSSING = 100;
 // DEFER_CROSSING is the hot loop of k_trace: the ray is on the inner sphere by construction (s.where is not looked at),
 // everything that involves the port edge happens in the kernel's slow path.
 template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
-__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, const SinCosTab& T, RayState& s, const HitDraws& dr) {
+__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, const DrawTabs& T, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
     if (DEFER_CROSSING || s.where == EV_WALL) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
     } else if (MODEL == 3) {
         d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
     } else if (MODEL == 1) {
-        d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s);
+        d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
     } else if (ROUGH) {
         d = lambert_in(T, n, t1, t2, dr.u_r, dr.q_phi);
     } else {
@@ -105,7 +105,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
 // turn out to hit the port edge (4 % of them) come back through the resume queue.
 // One 1024-thread block per SM (64 registers per thread): its shared memory holds the 64 kB sin/cos table
-// (altb_math.cuh: SinCosTab) and the two queues of each of its 32 warps.
+// (altb_math.cuh: DrawTabs) and the two queues of each of its 32 warps.
 static constexpr int TRACE_THREADS = 1024;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
@@ -123,7 +123,7 @@ static constexpr int XQCAP = 64, RQCAP = 96;
 // (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
 // loop any registers.
 template <bool ROUGH, int MODEL>
-__device__ __noinline__ int edge_bounces(const TraceParams& P, const SinCosTab& T, uint32_t id, RayState& t) {
+__device__ __noinline__ int edge_bounces(const TraceParams& P, const DrawTabs& T, uint32_t id, RayState& t) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
     int st;
     do {
@@ -137,7 +137,7 @@ __device__ __noinline__ int edge_bounces(const TraceParams& P, const SinCosTab& 
 
 struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
 
-static constexpr size_t TRACE_SMEM = SC_N * sizeof(float2) + (size_t)TRACE_WARPS * (XQCAP + RQCAP) * sizeof(QEntry);
+static constexpr size_t TRACE_SMEM = TABS_BYTES + (size_t)TRACE_WARPS * (XQCAP + RQCAP) * sizeof(QEntry);
 
 template <bool ROUGH, int MODEL>
 __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constant__ TraceParams P,
@@ -145,12 +145,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                                                          unsigned int* __restrict__ counter) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
     extern __shared__ __align__(16) unsigned char trace_smem[];
-    float2* s_tab = reinterpret_cast<float2*>(trace_smem);
-    QEntry* s_q = reinterpret_cast<QEntry*>(s_tab + SC_N);
-    for (int i = threadIdx.x; i < SC_N / 2; i += TRACE_THREADS)
-        reinterpret_cast<float4*>(s_tab)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
+    QEntry* s_q = reinterpret_cast<QEntry*>(trace_smem + TABS_BYTES);
+    for (int i = threadIdx.x; i < (int)(TABS_BYTES / sizeof(float4)); i += TRACE_THREADS)
+        reinterpret_cast<float4*>(trace_smem)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
     __syncthreads();
-    const SinCosTab T = {s_tab};
+    const DrawTabs T = make_tabs(trace_smem);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     QEntry* xq = s_q + (size_t)warp * (XQCAP + RQCAP);   // crossings waiting for the slow path
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(128) k_trace_generic(const __grid_constant__ T
     constexpr bool NEED_G = ROUGH || MODEL == 1;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const SinCosTab T = {P.sincos};
+    const DrawTabs T = make_tabs(P.sincos);
     RayState s;
     s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
     s.hits = 0; s.where = P.kind0;
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
                                                 altb_record* __restrict__ rec) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const SinCosTab T = {P.sincos};
+    const DrawTabs T = make_tabs(P.sincos);
     double d0[3], x0[3];
     const int kind0 = launch_ray(P.g, ray0 + 6 * (size_t)i, ray0 + 6 * (size_t)i + 3, d0, x0);
     RayState s;
@@ -723,7 +722,7 @@ __global__ void k_draws(const __grid_constant__ PhiloxKeys K, const float2* __re
                         int lobe_n, float lobe_ang, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SinCosTab T = {sincos};
+    const DrawTabs T = make_tabs(sincos);
     Draws d;
     make_draws<true>(K, T, ray_id0 + i, k, d);
     if (lobe_n > 0) d.u_r = lobe_accept(K, ray_id0 + i, k, lobe_n, lobe_ang);
@@ -734,13 +733,13 @@ __global__ void k_draws(const __grid_constant__ PhiloxKeys K, const float2* __re
 
 // ------------------------------------------------------------------------------------ math probe
 __global__ void k_probe_f32(int op, const float2* __restrict__ sincos, const float* __restrict__ x, uint32_t n, float* __restrict__ y) {
-    const SinCosTab T = {sincos};
+    const DrawTabs T = make_tabs(sincos);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float v = x[i];
         float s = 0.f, c = 0.f, r;
         if (op == 0) r = sqrt_c(v);
         else if (op == 1) r = rcp_c(v);
-        else if (op == 2) r = log_f32(v);
+        else if (op == 2) r = T.log_u20((uint32_t)v);
         else { T.at20((uint32_t)v & 0xfffffu, s, c); r = op == 3 ? s : c; }
         y[i] = r;
     }

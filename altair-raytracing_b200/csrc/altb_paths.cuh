@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) k_trace_paths(const __grid_constant__ Tra
     constexpr bool NEED_G = ROUGH || MODEL == 1;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const SinCosTab T = {P.sincos};
+    const DrawTabs T = make_tabs(P.sincos);
     float* p = pts + (size_t)i * max_points * 3;
     uint32_t np_ = 0;
     auto put = [&](const f3& v) {

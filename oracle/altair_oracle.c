@@ -211,35 +211,39 @@ void orc_sincos2pi_q20(uint32_t q, float* s, float* c) {
 static inline void sincos2pi_u13(float u, float* s, float* c) { orc_sincos2pi_q13((uint32_t)(u * 8192.0f), s, c); }
 static inline void sincos2pi_u20(float u, float* s, float* c) { orc_sincos2pi_q20((uint32_t)(u * 1048576.0f) & 0xfffffu, s, c); }
 
+/* Contract: |x| <= 0.9 is evaluated directly (quadrant 0 polynomials), anything larger is reduced first. */
 void orc_sincos_f32(float x, float* s, float* c) {
+    if (fabsf(x) <= 0.9f) { sincos_poly_f32(x, 0, s, c); return; }
     float q = rintf(x * 0.63661975f);
     float r = fmaf(q, -1.5707964f, x);
     r = fmaf(q, 4.3711388e-8f, r);
     sincos_poly_f32(r, (int)q, s, c);
 }
 
-float orc_log_f32(float x) {
-    uint32_t b = as_u(x);
-    int e = (int)(b >> 23) - 127;
-    float m = as_f((b & 0x007fffffu) | 0x3f800000u);
-    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
-    float z = m - 1.0f;
-    float z2 = z * z;
-    float p = 7.0376836292e-2f;
-    p = fmaf(p, z, -1.1514610310e-1f);
-    p = fmaf(p, z, 1.1676998740e-1f);
-    p = fmaf(p, z, -1.2420140846e-1f);
-    p = fmaf(p, z, 1.4249322787e-1f);
-    p = fmaf(p, z, -1.6668057665e-1f);
-    p = fmaf(p, z, 2.0000714765e-1f);
-    p = fmaf(p, z, -2.4999993993e-1f);
-    p = fmaf(p, z, 3.3333331174e-1f);
-    float fe = (float)e;
-    float y = (z * z2) * p;
-    y = fmaf(fe, -2.12194440e-4f, y);
-    y = fmaf(z2, -0.5f, y);
-    float r = z + y;
-    return fmaf(fe, 0.693359375f, r);
+/* ln(k 2^-20) for the 20-bit Box-Muller integer k = 1 .. 2^20 (csrc/altb_math.cuh: DrawTabs::log_u20): table over the
+ * top 7 mantissa bits of (float)k -- lg[hi] = (ln(m_hi'), 1/m_hi, e_adj), m_hi = 1 + hi/128, m_hi' = m_hi or m_hi/2
+ * (hi >= 53) -- plus a degree-4 log1p of the remainder. */
+static float g_lg_tab[128][3];
+__attribute__((constructor)) static void lg_tab_init(void) {
+    for (int hi = 0; hi < 128; hi++) {
+        double mh = 1.0 + hi / 128.0;
+        int half = hi >= 53;
+        g_lg_tab[hi][0] = (float)log(half ? mh * 0.5 : mh);
+        g_lg_tab[hi][1] = (float)(1.0 / mh);
+        g_lg_tab[hi][2] = half ? -146.0f : -147.0f;
+    }
+}
+float orc_log_u20(uint32_t k) {
+    uint32_t b = as_u((float)k);
+    const float* t = g_lg_tab[(b >> 16) & 0x7fu];
+    float base = fmaf((float)(b >> 23) + t[2], 0.69314718f, t[0]);
+    float mf = as_f((b & 0x007fffffu) | 0x3f800000u);
+    float mh = as_f((b & 0x007f0000u) | 0x3f800000u);
+    float r = (mf - mh) * t[1];
+    float q = fmaf(r, -0.25f, 0.33333334f);
+    q = fmaf(q, r, -0.5f);
+    q = fmaf(q, r, 1.0f);
+    return fmaf(q, r, base);
 }
 
 static inline void sincos2pi_d(double u, double* s, double* c) { double x = 2.0 * PI_D * u; *s = sin(x); *c = cos(x); }
@@ -259,9 +263,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* ONE Philox4x32-10 block (128 bits) per surface hit, counter = (ray_id lo, ray_id hi, k, 0), key = seed:
- *   w0: u_abs 24 b | 8 b -> bm_u1      w1: u_r 24 b | 8 b -> bm_u1
- *   w2: u_phi 20 b | 8 b -> u_sel | 4 b -> bm_u1
- *   w3: u_psi 13 b | bm_u2 13 b | 6 b -> u_sel
+ *   w0: u_abs 24 b | 8 b -> u_sel (low byte)      w1: u_r 24 b | 8 b -> bm_u1 (low byte)
+ *   w2: u_phi 20 b | 12 b -> bm_u1 (high bits)    w3: u_psi 13 b | bm_u2 13 b | 6 b -> u_sel (high bits)
  * (g0, g1) = Box-Muller of (bm_u1 in (0,1] with 20 bits, bm_u2 with 13 bits). */
 void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -271,11 +274,10 @@ void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_P
     out[0] = (float)(w[0] >> 8) * 0x1p-24f;
     out[1] = (float)(w[1] >> 8) * 0x1p-24f;
     out[2] = (float)(w[2] >> 12) * 0x1p-20f;
-    out[3] = (float)(((w[3] & 0x3fu) << 8) | ((w[2] >> 4) & 0xffu)) * 0x1p-14f;
+    out[3] = (float)(((w[3] & 0x3fu) << 8) | (w[0] & 0xffu)) * 0x1p-14f;
     out[4] = (float)(w[3] >> 19) * 0x1p-13f;
-    uint32_t t = ((w[0] & 0xffu) << 12) | ((w[1] & 0xffu) << 4) | (w[2] & 0xfu);
-    float u1 = (float)(t + 1u) * 0x1p-20f;                 /* (0,1] */
-    float rad = sqrtf(2.0f * fabsf(orc_log_f32(u1)));   /* log <= 0; |.| keeps u1 = 1 at +0 */
+    uint32_t t = ((w[2] & 0xfffu) << 8) | (w[1] & 0xffu);
+    float rad = sqrtf(2.0f * fabsf(orc_log_u20(t + 1u)));   /* u1 = (t+1) 2^-20 in (0,1]; log <= 0, |.| keeps u1 = 1 at +0 */
     float s, c;
     orc_sincos2pi_q13((w[3] >> 6) & 0x1fffu, &s, &c);
     out[5] = rad * c; out[6] = rad * s;

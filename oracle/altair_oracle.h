@@ -101,7 +101,7 @@ void  orc_sincos2pi_f32(float u, float* s, float* c);
 void  orc_sincos2pi_q13(uint32_t q, float* s, float* c);   /* table form, 13-bit turn fraction */
 void  orc_sincos2pi_q20(uint32_t q, float* s, float* c);   /* table + second-order rotation, 20-bit turn fraction */
 void  orc_sincos_f32(float x, float* s, float* c);
-float orc_log_f32(float x);
+float orc_log_u20(uint32_t k);   /* ln(k 2^-20), k = 1 .. 2^20 */
 
 /* Trace rays ray_id0 .. ray_id0+n-1 with Philox draws; rec and/or stats may be NULL. */
 int orc_trace(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,

@@ -100,8 +100,8 @@ def lib():
     L.orc_sincos_f32.argtypes = [C.c_float, P(C.c_float), P(C.c_float)]
     L.orc_sincos2pi_q13.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
     L.orc_sincos2pi_q20.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
-    L.orc_log_f32.argtypes = [C.c_float]
-    L.orc_log_f32.restype = C.c_float
+    L.orc_log_u20.argtypes = [C.c_uint32]
+    L.orc_log_u20.restype = C.c_float
     L.orc_trace.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
                             P(Stats), C.c_int]
     L.orc_trace_f64.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,

@@ -56,7 +56,7 @@ def test_f32_primitives_are_ieee_exact(ctx, oracle):
     """The written-out sqrt / reciprocal fast paths must be THE correctly rounded results (what sqrtf and 1.0f/x give on
     the CPU) on every argument the kernels can feed them: exhaustive over the 2^24 + 1 uniforms k 2^-24 (sqrt(u_r),
     sqrt(1 - u_r)), over every f32 in [1, 2] (orthonormal-basis reciprocal) and dense samples of the other ranges; the
-    log polynomial and the azimuth table must equal the oracle's restatement bit for bit."""
+    log and azimuth tables must equal the oracle's restatement bit for bit."""
     import ctypes as C
     rng = np.random.default_rng(3)
     u = (np.arange((1 << 24) + 1, dtype=np.float64) * 2.0 ** -24).astype(np.float32)
@@ -67,11 +67,9 @@ def test_f32_primitives_are_ieee_exact(ctx, oracle):
     for v in (m, -m, rng.uniform(0.4, 2.5, 4_000_000).astype(np.float32)):
         assert np.array_equal(ctx.probe_f32(1, v).view(np.uint32), (np.float32(1.0) / v).view(np.uint32))
     L = oracle.lib()
-    L.orc_log_f32.restype = C.c_float
-    t = rng.integers(1, (1 << 20) + 1, 60000)
-    u1 = (t.astype(np.float64) * 2.0 ** -20).astype(np.float32)
-    want = np.array([L.orc_log_f32(C.c_float(float(v))) for v in u1], dtype=np.float32)
-    assert np.array_equal(ctx.probe_f32(2, u1).view(np.uint32), want.view(np.uint32))
+    t = np.concatenate([rng.integers(1, (1 << 20) + 1, 60000), [1, 2, 3, (1 << 19) - 1, 1 << 19, (1 << 20) - 1, 1 << 20]])
+    want = np.array([L.orc_log_u20(int(v)) for v in t], dtype=np.float32)
+    assert np.array_equal(ctx.probe_f32(2, t.astype(np.float32)).view(np.uint32), want.view(np.uint32))
     q = np.concatenate([rng.integers(0, 1 << 20, 60000), np.arange(0, 1 << 20, 128)[:2000], [0, 127, (1 << 20) - 1]]).astype(np.uint32)
     s_, c_ = C.c_float(), C.c_float()
     ws, wc = np.zeros(q.size, np.float32), np.zeros(q.size, np.float32)

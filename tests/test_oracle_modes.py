@@ -41,10 +41,12 @@ def test_f32_primitives_accuracy(oracle):
         worst = max(worst, abs(s.value - np.sin(float(x))), abs(c.value - np.cos(float(x))))
     assert worst < 2e-6, worst
     worst = 0.0
-    for x in np.concatenate([rng.random(20000, dtype=np.float32) + np.float32(2 ** -24), np.float32([2 ** -24, 1.0, 0.5, 0.70710678])]):
-        got = L.orc_log_f32(float(x))
-        worst = max(worst, abs(got - np.log(float(x))) / max(1.0, abs(np.log(float(x)))))
+    for k in np.concatenate([rng.integers(1, (1 << 20) + 1, 20000), [1, 2, 3, 1 << 10, (1 << 19) - 1, 1 << 19, (1 << 20) - 1, 1 << 20]]):
+        got = L.orc_log_u20(int(k))
+        ref = np.log(int(k) * 2.0 ** -20)
+        worst = max(worst, abs(got - ref) / max(1.0, abs(ref)))
     assert worst < 3e-7, worst
+    assert L.orc_log_u20(1 << 20) == 0.0
 
 
 def test_draw_record_distribution(oracle):
