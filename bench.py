@@ -35,7 +35,7 @@ def workload_config(args, mode_name):
     return {"workload": "C3 nonLambertianFlux: CustomMirror BRDF (0.3,0.4,0.6), theta_max=170, rho=0.99, "
                         "sigma=0.01, src(-60,0,-75) dir(5,0,0), 180x90 map",
             "rays_per_gpu_per_step": args.rays, "map_mode": mode_name, "seed": 4357,
-            "l2": "working set (32 B/ray record buffer, 2 GiB per 2^26-ray batch) exceeds the 126 MB L2; "
+            "l2": "working set (32 B/ray record buffer, 8 GiB per 2^28-ray batch) exceeds the 126 MB L2; "
                   "the RNG is counter-based, there is no input to cache"}
 
 
@@ -192,7 +192,7 @@ def run_ours(args):
     _, kst = ctx.trace_fluxmap(sc, src, R, mp, seed=4357, ray_id0=step_no[0] * world * R + rank * R)
     kst = kst[0]
     peak = ctx.measure_fp32_peak()
-    n_batches = -(-R // (1 << 26))
+    n_batches = -(-R // (1 << 28))
     achieved = FLOP_PER_BOUNCE * kst["n_bounces"] / kst["t_trace_s"] * 1e-12
     roofline = {"bound": "fp32", "kernel": "k_trace<rough,CustomMirror>", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,

@@ -88,7 +88,7 @@ void altb_destroy(altb_ctx* ctx);
 const char* altb_last_error(void);
 int  altb_version(void);
 int  altb_device_count(void);
-/* batch = rays per trace launch (default 2^26); 0 keeps the default. */
+/* batch = rays per trace launch (default 2^28); 0 keeps the default. */
 int  altb_set_batch(altb_ctx* ctx, uint64_t batch_rays);
 
 /* THE HOT PATH.  For each scene: trace rays ray_id0 .. ray_id0+n_rays-1 (ray i's random stream

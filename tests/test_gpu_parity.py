@@ -205,6 +205,28 @@ def test_source_through_port_and_errors(ctx, oracle, altb):
         ctx.trace_records(altb.scene(brdf_kind=7), altb.source(), 10)
 
 
+def test_source_aimed_at_port_rim(ctx, oracle, altb):
+    """First event = the conical port edge (between r_inner and r_outer): fresh rays do not start on the inner sphere,
+    the library takes its generic one-thread-per-ray tracer; maps and records must still equal the oracle bit for bit."""
+    kw = dict(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=0.98, roughness=0.01, max_bounces=10000)
+    th = np.deg2rad(170.0)
+    q = 102.5 * np.array([np.sin(th), 0.0, np.cos(th)])            # a point on the edge, mid-wall
+    p0 = np.array([0.0, 0.0, -50.0])
+    for extra in (dict(), dict(brdf_kind=1, brdf_param=(0.3, 0.4, 0.6, 0.0))):
+        k2 = dict(kw, **extra)
+        g_src, o_src = altb.source(tuple(p0), tuple(q - p0)), oracle.source(tuple(p0), tuple(q - p0))
+        g_rec, g_st = ctx.trace_records(altb.scene(**k2), g_src, 20_000, seed=SEED)
+        o_rec, o_st = oracle.trace(oracle.scene(**k2), o_src, 20_000, seed=SEED, prec=oracle.F32)
+        assert _records_equal(g_rec, o_rec)
+        assert g_st["n_bounces"] == o_st["n_bounces"] and g_st["n_bounces"] > 20_000      # they do bounce (edge first)
+        g_counts, _ = ctx.trace_fluxmap(altb.scene(**k2), g_src, 20_000, altb.map_spec(mode=altb.MAP_DIRECTION), seed=SEED)
+        o_counts, _ = oracle.fluxmap(oracle.scene(**k2), o_src, 20_000, oracle.map_spec(mode=oracle.MAP_DIRECTION), seed=SEED,
+                                     prec=oracle.F32)
+        assert np.array_equal(g_counts[0], o_counts)
+    with pytest.raises(altb.AltbError):
+        ctx.trace_records(altb.scene(reflectance=-0.1), altb.source(), 10)
+
+
 def test_replay_bit_exact(ctx, oracle, altb):
     kw = dict(theta_max=170.0)
     n = 20_000
