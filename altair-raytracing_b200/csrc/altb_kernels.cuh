@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             }
             const unsigned cm = __ballot_sync(FULL, crossing);
             if (cm) {
-                if (nx + __popc(cm) > XQCAP) __trap();          // cannot happen (bounds above); never corrupt silently
                 if (crossing) {
                     QEntry e;
                     e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
