@@ -420,33 +420,59 @@ __device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const f3& d
 }
 
 static constexpr int DIR_THREADS = 512;
+// Only the escaping rays (43 % at 170 deg) need the double-precision acos/atan2 of the binning: each warp compacts them
+// into a 64-entry shared-memory queue (ballot + prefix popcount) and bins 32 at a time at full SIMT width.
 __global__ void __launch_bounds__(DIR_THREADS) k_map_direction(const altb_record* __restrict__ rec, uint32_t n,
                                                        const MapParams M,
                                                        unsigned long long* __restrict__ counts,
                                                        unsigned long long* __restrict__ stats,
                                                        int* __restrict__ bin_out) {
     extern __shared__ unsigned int hist[];
+    __shared__ float4 s_q[DIR_THREADS / 32][64];       // dir.xyz, record index
     const int nb = M.n_theta * M.n_phi;
     if (M.use_smem_hist) {
         for (int b = threadIdx.x; b < nb; b += blockDim.x) hist[b] = 0u;
         __syncthreads();
     }
-    StatAcc acc = {0, 0, 0, 0, 0, 0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        f3 pos, dir; uint32_t hits, status;
-        load_record(rec, i, pos, dir, hits, status);
-        const bool pf = port_flag(M.count_all, M.exit_zf, pos, status);
-        acc.add(hits, status, pf);
-        int b = -1;
-        if (pf) {
-            b = direction_bin(M.n_theta, M.n_phi, dir);
+    const unsigned lane = threadIdx.x & 31u;
+    float4* q = s_q[threadIdx.x >> 5];
+    uint32_t nq = 0;
+    auto bin_batch = [&](uint32_t first, uint32_t cnt) {       // entries [first, first+cnt), cnt <= 32
+        if (lane < cnt) {
+            const float4 e = q[first + lane];
+            const f3 dir = {e.x, e.y, e.z};
+            const int b = direction_bin(M.n_theta, M.n_phi, dir);
             if (b >= 0 && counts) {
                 if (M.use_smem_hist) atomicAdd(&hist[b], 1u);
                 else atomicAdd(counts + b, 1ull);
             }
+            if (bin_out) bin_out[__float_as_uint(e.w)] = b;
         }
-        if (bin_out) bin_out[i] = b;
+    };
+    StatAcc acc = {0, 0, 0, 0, 0, 0};
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool pf = false;
+        f3 dir = {0.f, 0.f, 0.f};
+        if (i < n) {
+            f3 pos; uint32_t hits, status;
+            load_record(rec, i, pos, dir, hits, status);
+            pf = port_flag(M.count_all, M.exit_zf, pos, status);
+            acc.add(hits, status, pf);
+            if (bin_out && !pf) bin_out[i] = -1;
+        }
+        const unsigned m = __ballot_sync(FULL, pf);
+        if (pf) q[nq + __popc(m & ((1u << lane) - 1u))] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((uint32_t)i));
+        nq += __popc(m);
+        __syncwarp();
+        if (nq >= 32) {
+            nq -= 32;
+            bin_batch(nq, 32);
+            __syncwarp();
+        }
     }
+    bin_batch(0, nq);
     if (stats) flush_stats(acc, stats);
     if (M.use_smem_hist && counts) {
         __syncthreads();
