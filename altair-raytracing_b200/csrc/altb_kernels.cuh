@@ -106,7 +106,10 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
 // turn out to hit the port edge (4 % of them) come back through the resume queue.
 // One 1024-thread block per SM (64 registers per thread): its shared memory holds the 64 kB sin/cos table
 // (altb_math.cuh: DrawTabs) and the two queues of each of its 32 warps.
-static constexpr int TRACE_THREADS = 1024;
+#ifndef ALTB_TRACE_THREADS
+#define ALTB_TRACE_THREADS 1024
+#endif
+static constexpr int TRACE_THREADS = ALTB_TRACE_THREADS;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
 #define ALTB_BOUNCES_PER_CHECK 2

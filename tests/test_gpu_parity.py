@@ -331,6 +331,22 @@ def test_statistics_vs_f64_physics_and_reference(ctx, oracle, altb):
     assert 0.6 < chi2 < 1.5, chi2
 
 
+@pytest.mark.parametrize("name,kw,n", [
+    ("c3", dict(theta_max=170.0, brdf_kind=1, brdf_param=(0.3, 0.4, 0.6, 0.0)), 16_000_000),
+    # deep, narrow port channel: ~1/3 of the crossings hit the conical edge -> the out-of-line edge bounces and the resume queue work hard
+    ("deep_port", dict(theta_max=176.0, r_outer=112.0, world_half=200.0, reflectance=0.995, roughness=0.01, max_bounces=10000), 4_000_000),
+])
+def test_large_run_bit_exact(ctx, oracle, altb, name, kw, n):
+    """Tens of millions of rays (1.6e9 surface hits in total) against the oracle's F32 mode: flux map and every counter equal exactly, so the rare
+    paths of the persistent kernel (queues, edge bounces, regeneration across chunks, kernel tail) are exercised at scale."""
+    gm, om = altb.map_spec(mode=altb.MAP_DIRECTION), oracle.map_spec(mode=oracle.MAP_DIRECTION)
+    g_counts, g_st = ctx.trace_fluxmap(altb.scene(**kw), altb.source(), n, gm, seed=SEED, ray_id0=1 << 34)
+    o_counts, o_st = oracle.fluxmap(oracle.scene(**kw), oracle.source(), n, om, seed=SEED, ray_id0=1 << 34, prec=oracle.F32)
+    assert np.array_equal(g_counts[0], o_counts)
+    for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+        assert g_st[0][key] == o_st[key], key
+
+
 def test_full_size_properties(ctx, altb):
     """BASELINE-size launch (1e8 rays, C5 per-scene size): conservation and GPU-count invariance."""
     n = 100_000_000
