@@ -125,9 +125,12 @@ static constexpr int XQCAP = 64, RQCAP = 96;
 // A ray on the port edge: bounce with the generic step until it is back on the inner sphere (returns 0) or ends
 // (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
 // loop any registers.
+extern __shared__ __align__(16) unsigned char trace_smem[];     // k_trace: draw tables, then the warps' queues
+
 template <bool ROUGH, int MODEL>
-__device__ __noinline__ int edge_bounces(const TraceParams& P, const DrawTabs& T, uint32_t id, RayState& t) {
+__device__ __noinline__ int edge_bounces(const TraceParams& P, uint32_t id, RayState& t) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
+    const DrawTabs T = make_tabs(trace_smem);      // rebuilt here: a reference argument would pin the caller's copy in local memory
     int st;
     do {
         HitDraws dr;
@@ -147,7 +150,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                                                          altb_record* __restrict__ rec,
                                                          unsigned int* __restrict__ counter) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
-    extern __shared__ __align__(16) unsigned char trace_smem[];
     QEntry* s_q = reinterpret_cast<QEntry*>(trace_smem + TABS_BYTES);
     for (int i = threadIdx.x; i < (int)(TABS_BYTES / sizeof(float4)); i += TRACE_THREADS)
         reinterpret_cast<float4*>(trace_smem)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     RayState t;
                     t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
                     t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
-                    const int st = edge_bounces<ROUGH, MODEL>(P, T, id, t);
+                    const int st = edge_bounces<ROUGH, MODEL>(P, id, t);
                     if (st) store_record(rec, id, t, st);
                     else {
                         resume = true;
