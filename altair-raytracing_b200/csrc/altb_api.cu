@@ -663,8 +663,8 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
 // ---------------------------------------------------------------------------------- replay
 template <bool R, int M>
 static void launch_replay_t(const ReplayParams& P, const double* ray0, const float4* tape, const unsigned long long* off,
-                            altb_record* rec, cudaStream_t st) {
-    k_replay<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, rec);
+                            const uint32_t* order, altb_record* rec, cudaStream_t st) {
+    k_replay<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, order, rec);
 }
 
 extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
@@ -683,8 +683,28 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
     const uint64_t n_rec = tape_off[n_rays];
     if (int rc = ensure(d.rec, d.rec_cap, n_rays)) return rc;
     double* d_ray0 = nullptr; float* d_tape = nullptr; unsigned long long* d_off = nullptr; int* d_bin = nullptr;
+    uint32_t* d_order = nullptr;
+    // schedule: longest tape first (counting sort by record count), so that the rays of a warp finish together
+    std::vector<uint32_t> order(n_rays);
+    {
+        uint64_t maxlen = 0;
+        for (uint64_t i = 0; i < n_rays; i++) {
+            if (tape_off[i + 1] < tape_off[i]) return fail(ALTB_E_ARG, "altb_replay: tape_off must be non-decreasing");
+            maxlen = std::max<uint64_t>(maxlen, tape_off[i + 1] - tape_off[i]);
+        }
+        const uint64_t nbk = std::min<uint64_t>(maxlen, 1u << 20) + 1;          // lengths above 2^20 share the first bucket
+        std::vector<uint64_t> start(nbk + 1, 0);
+        auto bucket = [&](uint64_t i) { return nbk - 1 - std::min<uint64_t>(tape_off[i + 1] - tape_off[i], nbk - 1); };
+        for (uint64_t i = 0; i < n_rays; i++) start[bucket(i) + 1]++;
+        for (uint64_t b = 0; b < nbk; b++) start[b + 1] += start[b];
+        for (uint64_t i = 0; i < n_rays; i++) order[start[bucket(i)]++] = (uint32_t)i;
+    }
     int rc = 0;
     do {
+        if (cudaMalloc(&d_order, n_rays * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpyAsync(d_order, order.data(), n_rays * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) {
+            rc = fail(ALTB_E_NOMEM, "altb_replay: cudaMalloc failed"); break;
+        }
         if (cudaMalloc(&d_ray0, n_rays * 6 * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&d_tape, std::max<uint64_t>(n_rec, 1) * 8 * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&d_off, (n_rays + 1) * sizeof(unsigned long long)) != cudaSuccess ||
@@ -697,15 +717,15 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
         const float4* t4 = reinterpret_cast<const float4*>(d_tape);
         cudaEventRecord(d.ev[0], d.stream);
         if (rough) {
-            if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else if (model == 2) launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else launch_replay_t<true, 3>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else if (model == 2) launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else launch_replay_t<true, 3>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
         } else {
-            if (model == 0) launch_replay_t<false, 0>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else if (model == 1) launch_replay_t<false, 1>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else if (model == 2) launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d.rec, d.stream);
-            else launch_replay_t<false, 3>(P, d_ray0, t4, d_off, d.rec, d.stream);
+            if (model == 0) launch_replay_t<false, 0>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else if (model == 1) launch_replay_t<false, 1>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else if (model == 2) launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+            else launch_replay_t<false, 3>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
         }
         cudaEventRecord(d.ev[1], d.stream);
         ctx->launches++;
@@ -736,7 +756,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
             for (uint64_t i = 0; i < n_rays; i++)
                 port[i] = (uint8_t)((P.g.count_all || out[i].status == ALTB_EXITED) && out[i].pos[2] < P.k.exit_zf);
     } while (0);
-    cudaFree(d_ray0); cudaFree(d_tape); cudaFree(d_off); cudaFree(d_bin);
+    cudaFree(d_ray0); cudaFree(d_tape); cudaFree(d_off); cudaFree(d_bin); cudaFree(d_order);
     return rc;
 }
 
