@@ -61,3 +61,21 @@ def test_product_never_imports_the_oracle():
                     if re.search(r"pyoracle|altair_oracle|orc_[a-z]+\(|oracle/", t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_hot_loop_has_no_spills(altb):
+    """Build-quality guard (no GPU needed): at 64 registers per thread ptxas is one temporary away from spilling inside
+    the bounce bodies of k_trace, which costs 15-20 % (profiles/README.md).  tools/sass_spills.py counts the local-memory
+    instructions between the Philox blocks of the unrolled loop; the roughness instances the benchmarks use must stay at
+    the handful that belong to the loop's edges."""
+    import shutil
+    import subprocess
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    altb.build_library()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_spills.py"), altb.library_path()],
+                         capture_output=True, text=True, check=True).stdout
+    inside = {m.group(1): int(m.group(2)) for m in re.finditer(r"k_trace<(\d,\d)>.*?: (\d+) in the bounce bodies", out)}
+    assert set(inside) >= {"1,0", "1,1"}, out
+    assert inside["1,0"] <= 4 and inside["1,1"] <= 4, out
