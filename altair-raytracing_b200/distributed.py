@@ -17,6 +17,12 @@ def shard_range(n_rays, rank, world):
     return lo, hi
 
 
+def owned_scenes(n_scenes, rank, world):
+    """Scene sharding (batched sweeps): scene k belongs to rank k mod world, so that the port-angle series --
+    whose cost per ray grows 40x along the series -- is dealt round-robin and every rank gets the same mix."""
+    return list(range(rank, n_scenes, world))
+
+
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -45,8 +51,14 @@ class ShardedTracer:
     map.  Device-resident: the kernels add into a torch int64 buffer on this rank's GPU and the
     all-reduce runs on the same stream right behind them."""
 
-    def __init__(self, ctx, scenes, src, mp, seed=4357, device=None):
+    def __init__(self, ctx, scenes, src, mp, seed=4357, device=None, shard="rays"):
+        """shard = "rays": every rank traces its slice of the ray ids of EVERY scene (balances a single big scene);
+        shard = "scenes": every rank traces ALL rays of the scenes it owns (owned_scenes) -- launches stay large when a
+        sweep has many scenes.  Ray ids are global either way, so both give the same integer maps."""
         import torch
+        if shard not in ("rays", "scenes"):
+            raise ValueError("shard must be 'rays' or 'scenes'")
+        self.shard = shard
         from .binding import Scene
         self.torch = torch
         self.ctx, self.src, self.mp, self.seed = ctx, src, mp, seed
@@ -63,12 +75,17 @@ class ShardedTracer:
         """Asynchronous; returns the device buffer (global sums after the all-reduce)."""
         torch = self.torch
         ns = len(self.scenes)
-        lo, hi = shard_range(n_rays, self.rank, self.world)
         self.buf.zero_()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         base = self.buf.data_ptr()
-        self.ctx.trace_fluxmap_dev(self.scenes, self.src, hi - lo, self.mp, base, base + 8 * ns * self.nb,
-                                   seed=self.seed, ray_id0=ray_id0 + lo, stream=stream)
+        if self.shard == "scenes" and self.world > 1:
+            for k in owned_scenes(ns, self.rank, self.world):       # the other ranks' slots stay zero; the sum fills them
+                self.ctx.trace_fluxmap_dev(self.scenes[k], self.src, n_rays, self.mp, base + 8 * k * self.nb,
+                                           base + 8 * (ns * self.nb + 8 * k), seed=self.seed, ray_id0=ray_id0, stream=stream)
+        else:
+            lo, hi = shard_range(n_rays, self.rank, self.world)
+            self.ctx.trace_fluxmap_dev(self.scenes, self.src, hi - lo, self.mp, base, base + 8 * ns * self.nb,
+                                       seed=self.seed, ray_id0=ray_id0 + lo, stream=stream)
         allreduce_counts(self.buf)
         return self.buf
 

@@ -48,6 +48,51 @@ def test_world_size_2_sharding_is_bit_identical(tmp_path, oracle):
         assert g["stats"][0] == N_RAYS and g["stats"][5] == st["n_bounces"] and g["stats"][2] == st["n_exit_port"]
 
 
+def _scene_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import pyoracle as O
+    from altair_raytracing_b200.distributed import merge_host_counts, owned_scenes
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    thetas = [150.0, 160.0, 170.0]
+    mp_ = O.map_spec(mode=O.MAP_DIRECTION)
+    nb = mp_.n_theta * mp_.n_phi
+    counts = np.zeros((len(thetas), nb), dtype=np.uint64)
+    vec = np.zeros(8 * len(thetas), dtype=np.uint64)
+    for k in owned_scenes(len(thetas), rank, world):            # whole scenes, all ray ids; the other slots stay zero
+        c, st = O.fluxmap(O.scene(theta_max=thetas[k]), O.source(), 6000, mp_, seed=SEED, prec=O.F32, n_threads=1)
+        counts[k] = c
+        vec[8 * k:8 * k + 6] = [st["n_rays"], st["n_exited"], st["n_exit_port"], st["n_absorbed"], st["n_suspended"], st["n_bounces"]]
+    g_counts, g_vec = merge_host_counts(counts, vec)
+    np.savez(os.path.join(out_dir, f"scene_rank{rank}.npz"), counts=g_counts, stats=g_vec)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_scene_sharding_is_bit_identical(tmp_path, oracle):
+    """Batched sweeps deal whole scenes round-robin (ShardedTracer(shard="scenes")): same single all-reduce, same maps."""
+    world = 2
+    mp.spawn(_scene_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"scene_rank{r}.npz") for r in range(world)]
+    for k, th in enumerate([150.0, 160.0, 170.0]):
+        full, st = oracle.fluxmap(oracle.scene(theta_max=th), oracle.source(), 6000, oracle.map_spec(mode=oracle.MAP_DIRECTION),
+                                  seed=SEED, prec=oracle.F32)
+        for g in got:
+            assert np.array_equal(g["counts"][k], full)
+            assert g["stats"][8 * k] == 6000 and g["stats"][8 * k + 5] == st["n_bounces"]
+
+
+def test_owned_scenes_partition():
+    sys.path.insert(0, ROOT)
+    from altair_raytracing_b200.distributed import owned_scenes
+    for n in (0, 1, 5, 160):
+        for w in (1, 2, 3, 8):
+            owned = [owned_scenes(n, r, w) for r in range(w)]
+            assert sorted(k for o in owned for k in o) == list(range(n))
+            assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
 def test_shard_range_partitions_exactly():
     sys.path.insert(0, ROOT)
     from altair_raytracing_b200.distributed import shard_range
