@@ -49,23 +49,25 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
         nrm.x = (float)nn[0]; nrm.y = (float)nn[1]; nrm.z = (float)nn[2];
     }
     if (dr.absorb) return ALTB_ABSORBED;
-    f3 n = nrm, t1, t2;
-    if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n, t1, t2);
     f3 d;
-    if (MODEL == 2) {
-        float m = -2.0f * dot3(s.dir, n);
-        d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
-    } else if (MODEL == 3) {
-        d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
-    } else if (MODEL == 1) {
-        d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
-    } else if (ROUGH) {
-        d = lambert_in(T, n, t1, t2, dr.u_r, dr.q_phi);
+    float dn;
+    if (MODEL == 0) {                  // Lambert: composed in the local frame of the true normal, d.nrm falls out
+        if (ROUGH) d = lambert_tilted(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, dr.u_r, dr.q_phi, dn);
+        else d = lambert_dir(T, nrm, dr.u_r, dr.q_phi, dn);
     } else {
-        d = lambert_dir(T, n, dr.u_r, dr.q_phi);
+        f3 n = nrm;
+        if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n);
+        if (MODEL == 2) {
+            float m = -2.0f * dot3(s.dir, n);
+            d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
+        } else if (MODEL == 3) {
+            d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
+        } else {
+            d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
+        }
+        dn = dot3(d, nrm);
     }
-    float dn = dot3(d, nrm);
-    if (dn < 0.0f) {
+    if ((MODEL != 0 || ROUGH) && dn < 0.0f) {      // keep the new direction on the incoming side of the TRUE surface
         float m = -2.0f * dn;
         d.x = fma_(m, nrm.x, d.x); d.y = fma_(m, nrm.y, d.y); d.z = fma_(m, nrm.z, d.z);
         dn = -dn;
