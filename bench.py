@@ -113,6 +113,22 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # stdout carries exactly ONE line, the JSON: libraries that write to fd 1 on their own (NCCL prints its version banner
+    # at the first communicator when NCCL_DEBUG is set on the box) are sent to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_ours(args):
     import ctypes as C
     import numpy as np
     import torch
@@ -211,7 +227,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.map),
@@ -236,9 +252,9 @@ def run_ours(args):
                                               f"run here), {cdt:.1f} s"}
         except Exception as e:          # the CPU leg must never cost the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
