@@ -103,6 +103,9 @@ struct Ctx {
             std::cerr << "Error: " << altb_last_error() << std::endl;
             h = nullptr;
         }
+        // a macro call makes and drops its own context: 2^26-ray launches (2 GiB of records) keep the allocation and its
+        // release cheap; the library default (2^28) only pays off for long-lived contexts
+        if (h) altb_set_batch(h, 1ull << 26);
     }
     ~Ctx() { if (h) altb_destroy(h); }
 };
@@ -203,17 +206,16 @@ bool writePerPositionFile(const std::string& fullPath, const std::string& startS
             double phi1 = (j + 0.5) * 360.0 / nPhiBins;
             double fraction1 = double(counts[(size_t)i * nPhiBins + j]) / double(n);
             totalHitRays += (long long)counts[(size_t)i * nPhiBins + j];
-            csvFile << std::fixed << std::setprecision(6) << theta << "," << phi1 << "," << fraction1 << std::endl;
+            csvFile << std::fixed << std::setprecision(6) << theta << "," << phi1 << "," << fraction1 << '\n';   // same bytes as std::endl, no write() per row
             if (twofold) {
                 int j2 = j + nPhiBins / 2;
                 double phi2 = phi1 + 180.0;
                 if (phi2 >= 360.0) phi2 -= 360.0;
                 double fraction2 = double(counts[(size_t)i * nPhiBins + j2]) / double(n);
                 totalHitRays += (long long)counts[(size_t)i * nPhiBins + j2];
-                csvFile << std::fixed << std::setprecision(6) << theta << "," << phi2 << "," << fraction2 << std::endl;
+                csvFile << std::fixed << std::setprecision(6) << theta << "," << phi2 << "," << fraction2 << '\n';
             }
         }
-        csvFile.flush();
     }
     csvFile << "# Sweep completed at: " << nowString() << std::endl;
     csvFile << "# Total execution time: " << realTime << " seconds" << std::endl;
