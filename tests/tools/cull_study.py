@@ -1,3 +1,5 @@
+"""LINE-map culling study (lives under tests/ because it takes its exit rays from the oracle): hits, per-bin sphere-criterion
+passes and lane-tests per escaping ray for the candidate tile shapes.  Run from the repository root."""
 import sys
 sys.path.insert(0,'oracle'); sys.path.insert(0,'.')
 import numpy as np, pyoracle as O

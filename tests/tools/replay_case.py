@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Replay-mode measurement: record a tape with the CPU oracle (test infrastructure, allowed in tools used by tests
-and benchmarks only), replay it on the GPU, check it against the Philox run, print the kernel's tape bandwidth
+"""Replay-mode measurement (lives under tests/ because it uses the oracle, which is test infrastructure): record a tape
+with the CPU oracle, replay it on the GPU, check it against the Philox run, print the kernel's tape bandwidth
 (ALTB_TIMING=1).  The replay kernel is the one HBM-bound kernel of the path: 32 B of recorded draws per surface hit."""
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 os.environ["ALTB_TIMING"] = "1"
 import altair_raytracing_b200 as A  # noqa: E402
