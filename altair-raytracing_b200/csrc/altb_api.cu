@@ -619,6 +619,7 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
                                    uint64_t n_rays, uint64_t seed, const double* det_center, const double* det_rot,
                                    uint32_t m, double det_r, double det_halfthick, uint64_t* hits, altb_stats* stats) {
     if (!ctx || !scene || !src || !det_center || !det_rot || !hits || m == 0) return fail(ALTB_E_ARG, "altb_detector_sweep: NULL/empty argument");
+    if (m > 2048) return fail(ALTB_E_ARG, "altb_detector_sweep: at most 2048 poses per call (per-block shared-memory tables)");
     DevCtx& d = ctx->devs[0];
     CK(cudaSetDevice(d.dev));
     TraceSetup ts;
@@ -643,7 +644,8 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
             int blocks = d.sm_count * 4;
             const int need = (int)((n + 7) / 8);
             if (blocks > need) blocks = need;
-            k_disk_hits<<<blocks, 256, 0, d.stream>>>(d.rec, n, ts.P.g, d_geo, d_geo + (size_t)m * 3, m, det_r, det_halfthick, d_hits);
+            k_disk_hits<<<blocks, DISK_THREADS, (size_t)m * (sizeof(float4) + sizeof(unsigned int)), d.stream>>>(d.rec, n, ts.P.g, d_geo, d_geo + (size_t)m * 3, m, det_r,
+                                                                                                   det_halfthick, d_hits);
             ctx->launches += 2;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ALTB_E_CUDA, "detector_sweep: launch failed");
         }
