@@ -42,7 +42,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
     s.hits += 1;
     f3 nrm;
     if (DEFER_CROSSING || s.where == EV_WALL) {
-        nrm.x = s.pos.x * k.neg_inv_r1; nrm.y = s.pos.y * k.neg_inv_r1; nrm.z = s.pos.z * k.neg_inv_r1;
+        nrm = scale3(k.neg_inv_r1, s.pos);
     } else {
         double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z}, nn[3];
         edge_normal(g, q, nn);
@@ -68,8 +68,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
         dn = dot3(d, nrm);
     }
     if ((MODEL != 0 || ROUGH) && dn < 0.0f) {      // keep the new direction on the incoming side of the TRUE surface
-        float m = -2.0f * dn;
-        d.x = fma_(m, nrm.x, d.x); d.y = fma_(m, nrm.y, d.y); d.z = fma_(m, nrm.z, d.z);
+        d = axpy3(-2.0f * dn, nrm, d);
         dn = -dn;
     }
     if (s.hits >= (uint32_t)g.max_bounces) { s.dir = d; return ALTB_SUSPENDED; }
@@ -77,9 +76,8 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
     double out[3];
     if (DEFER_CROSSING || s.where == EV_WALL) {
         float t = k.two_r1 * dn;
-        f3 x = {fma_(t, d.x, s.pos.x), fma_(t, d.y, s.pos.y), fma_(t, d.z, s.pos.z)};
-        float sc = fma_(dot3(x, x), k.nr_c, 1.5f);
-        x.x *= sc; x.y *= sc; x.z *= sc;
+        f3 x = axpy3(t, d, s.pos);
+        x = scale3(fma_(dot3(x, x), k.nr_c, 1.5f), x);
         s.pos = x; s.dir = d;
         if (x.z >= k.zc) return 0;                                   // fast path: wall to wall
         if (DEFER_CROSSING) return ST_CROSSING;
