@@ -214,14 +214,14 @@ def _run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 2^28-ray launch of this kernel, from the
                 # `ncu --set full` capture in profiles/r01_ncu_final.md (algorithmic: 2^28 rays x 32 B = 8.590e9 B)
-                "traffic": 9.4241e9, "traffic_unit": "B per 2^28-ray launch (ncu, profiles/r01_ncu_final.md)",
+                "traffic": 9.4184e9, "traffic_unit": "B per 2^28-ray launch (ncu, profiles/r01_ncu_final.md)",
                 "peak_source": "FFMA-chain probe measured live on this GPU (MEASURED_PEAKS.json has no FP32 number); "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "flop_per_bounce": FLOP_PER_BOUNCE, "launches": n_batches,
                 "avg_launch_ms": kst["t_trace_s"] * 1e3 / n_batches, "map_ms_per_launch": kst["t_map_s"] * 1e3 / n_batches,
                 "bounces_per_s_kernel": kst["n_bounces"] / kst["t_trace_s"],
-                "issue_slots_busy_ncu": 0.826, "active_lanes_ncu": 27.75, "fma_pipe_ncu": 0.54, "alu_pipe_ncu": 0.51,
-                "warp_instructions_per_bounce_ncu": 299,
+                "issue_slots_busy_ncu": 0.823, "active_lanes_ncu": 27.6, "fma_pipe_ncu": 0.54, "alu_pipe_ncu": 0.52,
+                "warp_instructions_per_bounce_ncu": 296,
                 "hbm_bytes_per_bounce_algorithmic": 32.0 * kst["n_rays"] / kst["n_bounces"]}
     barrier()
     if rank != 0:
