@@ -124,7 +124,8 @@ int altb_trace_paths(altb_ctx* ctx, const altb_scene* scene, const altb_source* 
 
 /* Physical thin-disk detectors, traced once and tested against all m poses.  Replaces the
  * per-position re-trace of integratingSphereDetectorSweep.C:31-105,134-172.
- * det_rot[m][9] row-major TGeoRotation matrices, det_center[m][3]. hits[m] is added to. */
+ * det_rot[m][9] row-major TGeoRotation matrices, det_center[m][3]. hits[m] is added to.  m <= 2048 per call
+ * (the reference sweeps 362 poses); split larger sweeps over calls with the same seed and ray ids. */
 int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
                         uint64_t n_rays, uint64_t seed, const double* det_center, const double* det_rot,
                         uint32_t m, double det_r, double det_halfthick, uint64_t* hits, altb_stats* stats);
