@@ -57,20 +57,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside the timed region [t0, t1] (host clock); a region shorter than the sampling period falls back
+        to the samples closest to it (the sampler runs from before the warm-up on)."""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 pass
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        rows = [r for r in self.rows if len(r) > 3 and r[2].isdigit()]
+        if t0 is not None and rows:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.25]
+            rows = inside if inside else sorted(rows, key=lambda r: abs(r[0] - t1))[:2]
+        rows = [r[1:] for r in rows]
+        sm = sorted(int(r[1]) for r in rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in rows if len(r) > 2 and r[2].isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -163,13 +170,14 @@ def _run_ours(args):
         step_no[0] += 1
         return buf
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         one_step()
     barrier()
     l0 = ctx.launches
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    t_region0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -181,7 +189,7 @@ def _run_ours(args):
     barrier()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_region0, time.time()) if rank == 0 else None
     launches = ctx.launches - l0 + (args.steps if world > 1 else 0)   # + the all-reduce kernels
     dt = ms.item() * 1e-3
     st = total.cpu().numpy()
