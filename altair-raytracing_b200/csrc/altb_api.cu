@@ -242,6 +242,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, uint64_t ray_id0,
     // ids are claimed in chunks; small enough that the tail (last chunk per warp) stays short
     uint32_t chunk = 256;
     while (chunk > 32 && (uint64_t)chunk * blocks * TRACE_WARPS * 4 > n) chunk >>= 1;
+    if (const char* e = getenv("ALTB_CHUNK")) { const long v = atol(e); if (v >= 32 && v <= 65536) chunk = (uint32_t)v; }   // tuning knob
     P.chunk = chunk;
     CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
     cudaError_t le = cudaSuccess;
