@@ -258,6 +258,10 @@ def _run_ours(args):
             line["cpu_baseline"] = {"value": ost["n_bounces"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} rays of the same workload, FP64 oracle restatement (ROOT+ROBAST cannot "
                                               f"run here), {cdt:.1f} s"}
+            s1 = max(sample // (2 * max(cores, 1)), 1000)          # the same on ONE core, ~half the time again
+            t0 = time.perf_counter()
+            _, ost1 = O.fluxmap(osc, osrc, s1, omp_, seed=4357, prec=O.F64, n_threads=1)
+            line["cpu_baseline"]["value_1core"] = ost1["n_bounces"] / (time.perf_counter() - t0)
         except Exception as e:          # the CPU leg must never cost the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if world > 1:
