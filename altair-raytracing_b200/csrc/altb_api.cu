@@ -36,6 +36,12 @@ struct DevCtx {
     float4* tiles = nullptr; uint64_t tiles_cap = 0;
     float4* lines = nullptr; uint64_t lines_cap = 0;    // dense list of escaping rays for the line maps (2 float4 each)
     float2* sincos = nullptr;                           // SC_N-entry azimuth table (altb_math.cuh: SinCosTab)
+    // second record buffer + counter + two worker streams: consecutive launches of a DIRECTION-mode job alternate between
+    // them, so that the tail of one persistent launch (its last long rays) overlaps the start of the next one
+    altb_record* rec2 = nullptr; uint64_t rec2_cap = 0;
+    unsigned int* counter2 = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -118,6 +124,10 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.sincos);
+        cudaFree(d.rec2); cudaFree(d.counter2);
+        for (auto& a : d.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+        if (d.fork_ev) cudaEventDestroy(d.fork_ev);
+        for (auto& e : d.join_ev) if (e) cudaEventDestroy(e);
         for (auto& e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -146,6 +156,12 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&d.counter2, sizeof(unsigned int)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.aux[0], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.aux[1], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.join_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.join_ev[1], cudaEventDisableTiming) != cudaSuccess ||
             cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&d.sincos, TABS_BYTES) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
@@ -443,20 +459,43 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
     const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
     const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n_rays, 1));
     if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
-    for (int s = 0; s < n_scenes; s++) {
+    // Two launches in flight (see DevCtx): only where nothing but the records and the counter are per-launch state
+    // (DIRECTION maps) and nobody asked for per-kernel timings.
+    const uint64_t n_launches = (uint64_t)n_scenes * ((n_rays + batch - 1) / batch);
+    const bool overlap = !t_trace_ms && map->map_mode == ALTB_MAP_DIRECTION && n_launches >= 2 && !getenv("ALTB_NO_OVERLAP");
+    if (overlap) {
+        if (int rc = ensure(d.rec2, d.rec2_cap, batch)) return rc;
+        CK(cudaEventRecord(d.fork_ev, st));
+        CK(cudaStreamWaitEvent(d.aux[0], d.fork_ev, 0));
+        CK(cudaStreamWaitEvent(d.aux[1], d.fork_ev, 0));
+    }
+    altb_record* const rec_main = d.rec;
+    unsigned int* const counter_main = d.counter;
+    uint64_t launch_no = 0;
+    int rc_all = 0;
+    for (int s = 0; s < n_scenes && !rc_all; s++) {
         TraceSetup ts;
-        if (int rc = setup_trace(&scenes[s], src, seed, ts)) return rc;
+        if ((rc_all = setup_trace(&scenes[s], src, seed, ts))) break;
         MapSetup ms;
-        if (int rc = setup_map(d, &scenes[s], ts.P.g, ts.P.k, map, ms, st)) return rc;
+        if ((rc_all = setup_map(d, &scenes[s], ts.P.g, ts.P.k, map, ms, st))) break;
         float tt = 0.f, tm = 0.f;
-        for (uint64_t off = 0; off < n_rays; off += batch) {
+        for (uint64_t off = 0; off < n_rays && !rc_all; off += batch, launch_no++) {
             const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
-            if (t_trace_ms) CK(cudaEventRecord(d.ev[0], st));
-            if (int rc = run_trace(ctx, d, ts, ray_id0 + off, n, st)) return rc;
-            if (t_trace_ms) CK(cudaEventRecord(d.ev[1], st));
-            if (int rc = run_map(ctx, d, ms, n, ray_id0 + off, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, st)) return rc;
-            if (t_trace_ms) {
-                CK(cudaEventRecord(d.ev[2], st));
+            cudaStream_t ls = st;
+            if (overlap) {                              // run_trace / run_map read the buffers from the context
+                const int slot = (int)(launch_no & 1);
+                ls = d.aux[slot];
+                d.rec = slot ? d.rec2 : rec_main;
+                d.counter = slot ? d.counter2 : counter_main;
+            }
+            if (t_trace_ms) CK(cudaEventRecord(d.ev[0], ls));
+            rc_all = run_trace(ctx, d, ts, ray_id0 + off, n, ls);
+            if (!rc_all && t_trace_ms) CK(cudaEventRecord(d.ev[1], ls));
+            if (!rc_all)
+                rc_all = run_map(ctx, d, ms, n, ray_id0 + off, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, ls);
+            d.rec = rec_main; d.counter = counter_main;
+            if (!rc_all && t_trace_ms) {
+                CK(cudaEventRecord(d.ev[2], ls));
                 CK(cudaEventSynchronize(d.ev[2]));
                 float a = 0.f, b = 0.f;
                 CK(cudaEventElapsedTime(&a, d.ev[0], d.ev[1]));
@@ -466,7 +505,13 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
         }
         if (t_trace_ms) { t_trace_ms[s] = tt; t_map_ms[s] = tm; }
     }
-    return 0;
+    if (overlap) {                                      // join, also on the error path
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventRecord(d.join_ev[i], d.aux[i]));
+            CK(cudaStreamWaitEvent(st, d.join_ev[i], 0));
+        }
+    }
+    return rc_all;
 }
 
 extern "C" int altb_trace_fluxmap_dev(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
