@@ -1,10 +1,12 @@
 // altb_kernels.cuh -- sm_100a kernels of the integrating-sphere hot path.
 //   K1  k_trace        persistent warps with ray regeneration: source -> bounce loop -> 32-byte record
+//       k_trace_generic  one thread per ray, for sources whose first event is the port rim
 //   K1r k_replay       same state machine, draws streamed from a recorded tape
-//   K2a k_map_direction  records -> stats + one-bin-per-ray direction map (shared-memory histogram)
-//   K2b k_map_line     records -> 16 200 overlapping line-disk tests per ray, culled by tiles,
+//   K2a k_map_direction  records -> stats + one-bin-per-ray direction map (warp-compacted binning, shared-memory histogram)
+//   K2b k_compact_exits + k_map_line  records -> 16 200 overlapping line-disk tests per ray, culled by tiles,
 //                      bin-stationary register accumulation (no atomics in the inner loop)
-//   K2c k_stats, K2d k_disk_hits, k_draws, k_fill_records
+//   K2c k_map_per_position, k_stats   K2d k_disk_hits (f32 pre-test + compacted FP64 tests)
+//       k_make_sincos_table, k_draws, k_probe_f32, k_fill_records, k_fma_peak
 // What they replace in the reference: ROBAST AOpticsManager::TraceNonSequential as called from
 // flux_at_observer/fluxAtObserverFast.C:1153 / fluxAtObserverOptimize.C:295, and the host loops
 // fluxAtObserverFast.C:1164-1303 (endpoint extraction + detector sweep).
@@ -103,9 +105,10 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
 // opening: cone-edge test + world-box exit -- is not done in line (it would run with ~1 active lane in
 // every fifth iteration): the lane parks (crossing point, direction, id, hits) in the warp's shared-memory
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
-// turn out to hit the port edge (4 % of them) come back through the resume queue.
-// One 1024-thread block per SM (64 registers per thread): its shared memory holds the 64 kB sin/cos table
-// (altb_math.cuh: DrawTabs) and the two queues of each of its 32 warps.
+// turn out to hit the port edge (4 % of them) bounce there out of line (edge_bounces) and come back through
+// the resume queue once they are on the inner sphere again.
+// One 1024-thread block per SM (64 registers per thread): its shared memory holds the draw tables (64 kB
+// sin/cos + 2 kB log, altb_math.cuh: DrawTabs) and the two queues of each of its 32 warps.
 #ifndef ALTB_TRACE_THREADS
 #define ALTB_TRACE_THREADS 1024
 #endif
@@ -122,11 +125,11 @@ static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 // and every crossing frees a lane, so the resume queue holds at most the crossing backlog plus one pass: nr <= 63 + 32.
 static constexpr int XQCAP = 64, RQCAP = 96;
 
+extern __shared__ __align__(16) unsigned char trace_smem[];     // k_trace: draw tables, then the warps' queues
+
 // A ray on the port edge: bounce with the generic step until it is back on the inner sphere (returns 0) or ends
 // (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
 // loop any registers.
-extern __shared__ __align__(16) unsigned char trace_smem[];     // k_trace: draw tables, then the warps' queues
-
 template <bool ROUGH, int MODEL>
 __device__ __noinline__ int edge_bounces(const TraceParams& P, const DrawTabs& T, uint32_t id, RayState& t) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;     // (T by reference: rebuilding it from trace_smem here measured 1.3 % slower)
@@ -140,7 +143,7 @@ __device__ __noinline__ int edge_bounces(const TraceParams& P, const DrawTabs& T
     return st;
 }
 
-struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits(|where<<31)
+struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits
 
 static constexpr size_t TRACE_SMEM = TABS_BYTES + (size_t)TRACE_WARPS * (XQCAP + RQCAP) * sizeof(QEntry);
 
