@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the integrating-sphere hot path (BASELINE.json config C3).
 
-A "step" = one pass of the hot path over one batch of synthetic source rays PER GPU:
+A "step" = one pass of the hot path over one batch of synthetic source rays:
 trace (source -> multi-bounce loop with the CustomMirror BRDF) + 180x90 flux map + (N>1) one all-reduce.
-Metric = ray-bounces/s summed over all GPUs ("scaling": "weak": each GPU gets --rays rays per step).
+Metric = ray-bounces/s of the whole job.  Default "scaling": "strong" -- BASELINE.json configs[2]: the SAME
+1e9 rays per step on 1/2/4/8 GPUs (the reference's analogue is SetMaxThreads on a fixed ray count,
+fluxAtObserverFast.C:1083-1087); --scaling weak gives every GPU --rays rays per step.  The line carries both rates
+(`other_scaling`) and `map_crc`, the CRC-32 of the all-reduced map of a fixed 1e7-ray probe: equal at every N.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--map direction|line] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--scaling strong|weak] [--map direction|line]
+                  [--impl reference]
   N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 """
 import argparse
@@ -21,8 +25,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ray_bounces_per_s_fluxmap"
 UNIT = "ray-bounces/s"
-FLOP_PER_BOUNCE = 100.0          # Lambert + Gaussian-roughness configuration
+FLOP_PER_BOUNCE = 100.0          # SURVEY.md 8(d)'s per-unit figure (Lambert + Gaussian roughness): the contract's unit of work
+FLOP_PER_BOUNCE_MODEL = 117.0    # the CustomMirror step actually benched, counted from csrc/altb_math.cuh
 REF_RECORDED = 3.7e6             # reference's own recorded rate, author's PC, <=4 threads
+C3_RAYS = 1_000_000_000          # BASELINE.json configs[2]
+PROBE_RAYS = 10_000_000          # map_crc probe
 
 
 def workload_scene(mod):
@@ -31,12 +38,21 @@ def workload_scene(mod):
                      brdf_kind=1, brdf_param=(0.3, 0.4, 0.6, 0.0))
 
 
-def workload_config(args, mode_name):
+def workload_config(args, mode_name, world):
+    total = args.rays if args.scaling == "strong" else args.rays * world
     return {"workload": "C3 nonLambertianFlux: CustomMirror BRDF (0.3,0.4,0.6), theta_max=170, rho=0.99, "
                         "sigma=0.01, src(-60,0,-75) dir(5,0,0), 180x90 map",
-            "rays_per_gpu_per_step": args.rays, "map_mode": mode_name, "seed": 4357,
-            "l2": "working set (32 B/ray record buffer, 8 GiB per 2^28-ray batch) exceeds the 126 MB L2; "
-                  "the RNG is counter-based, there is no input to cache"}
+            "rays_per_step": total, "rays_per_gpu_per_step": total // world, "map_mode": mode_name, "seed": 4357,
+            "l2": "no input to cache: the RNG is counter-based and every step traces NEW ray ids, so nothing a step reads "
+                  "was produced by an earlier one; per-step device traffic is the map/stats buffer only"}
+
+
+def host_threads():
+    """Cores this process may use -- NOT omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -85,9 +101,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_rate_probe(O, sc, src, mp, threads):
+    """(ray-bounces/s, bounces per ray) of the CPU path on `threads` threads: slope between two short runs, so that the
+    fixed cost of a call (buffers, thread start-up: ~0.4 s) does not bias the bounded samples sized from it."""
+    O.fluxmap(sc, src, 100_000, mp, seed=4357, ray_id0=1 << 41, prec=O.F64, n_threads=threads)      # cold start: threads, page faults
+    pts, n = [], 50_000
+    for _ in range(8):
+        t0 = time.perf_counter()
+        _, st = O.fluxmap(sc, src, n, mp, seed=4357, ray_id0=1 << 40, prec=O.F64, n_threads=threads)
+        pts.append((time.perf_counter() - t0, st["n_bounces"], st["n_rays"]))
+        if len(pts) >= 2 and pts[-1][0] - pts[-2][0] >= 0.5:
+            break
+        n *= 4
+    (t1, b1, _), (t2, b2, r2) = (pts[-2] if len(pts) > 1 else (0.0, 0, 0)), pts[-1]
+    rate = max((b2 - b1) / max(t2 - t1, 1e-3), b2 / t2)
+    return rate, b2 / max(r2, 1)
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  ROOT + ROBAST cannot be built here
-    (DESIGN.md), so this times the oracle's double-precision restatement on all host cores."""
+    (DESIGN.md), so this times the oracle's double-precision restatement on all host cores.  The thread count is
+    explicit (torchrun exports OMP_NUM_THREADS=1) and every step is a bounded sample of the workload, sized from a
+    half-second calibration so that warm-up + K steps take about --ref-budget seconds whatever K and the core count are."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -96,24 +131,30 @@ def run_reference(args):
     O.build()
     mode = O.MAP_DIRECTION if args.map == "direction" else O.MAP_LINE
     sc, src, mp = workload_scene(O), O.source(), O.map_spec(mode=mode)
-    cores = O.lib().orc_num_threads()
-    sample = args.ref_rays
+    cores = host_threads()
+    if args.ref_rays > 0:
+        sample = args.ref_rays
+    else:
+        rate, bpr = cpu_rate_probe(O, sc, src, mp, cores)
+        per_step = args.ref_budget / (args.steps + 0.1 * args.warmup)
+        sample = int(min(max(rate * per_step / bpr, 2_000), 50_000_000))
     for w in range(args.warmup):
-        O.fluxmap(sc, src, max(sample // 10, 1000), mp, seed=4357, ray_id0=w * sample, prec=O.F64, n_threads=0)
+        O.fluxmap(sc, src, max(sample // 10, 1000), mp, seed=4357, ray_id0=w * sample, prec=O.F64, n_threads=cores)
     bounces = 0
     t0 = time.perf_counter()
     for s in range(args.steps):
-        _, st = O.fluxmap(sc, src, sample, mp, seed=4357, ray_id0=(args.warmup + s) * sample, prec=O.F64, n_threads=0)
+        _, st = O.fluxmap(sc, src, sample, mp, seed=4357, ray_id0=(args.warmup + s) * sample, prec=O.F64, n_threads=cores)
         bounces += st["n_bounces"]
     dt = time.perf_counter() - t0
     v = bounces / dt
-    cfg = workload_config(args, args.map)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = workload_config(args, args.map, world)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} rays per step of the same workload ({bounces} bounces in {dt:.1f} s); "
-                                       "ROOT+ROBAST are not installable here, this is the FP64 oracle restatement"},
+                             "sample": f"{sample} rays per step of the same workload ({bounces} bounces in {dt:.1f} s on "
+                                       f"{cores} threads); ROOT+ROBAST are not installable here, this is the FP64 oracle restatement"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "rays_per_s": sample * args.steps / dt, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -135,8 +176,25 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
+def profile_reference():
+    """ncu-derived numbers are NOT measured by this run: they are read from the committed capture summary
+    (profiles/*_k_trace_ncu.json, written by tools/ncu_summary.py --json) together with the capture's own configuration."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_trace_ncu.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        d["file"] = os.path.relpath(files[-1], ROOT)
+        return d
+    except Exception:
+        return None
+
+
 def _run_ours(args):
     import ctypes as C
+    import zlib
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -153,47 +211,48 @@ def _run_ours(args):
     sc, src, mp = workload_scene(A), A.source(), A.map_spec(mode=mode)
     ctx = A.Context([local])
     tr = ShardedTracer(ctx, sc, src, mp, seed=4357, device=local)
-    R = args.rays
     nb = mp.n_theta * mp.n_phi
+    next_id = [0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    total = torch.zeros(8, dtype=torch.int64, device=tr.device)
-    step_no = [0]
-
-    def one_step():
-        # weak scaling: the job traces world*R rays per step, this rank its shard of them
-        buf = tr.step_device(world * R, ray_id0=step_no[0] * world * R)
-        step_no[0] += 1
+    def step_dev(total):
+        """one step of the job: `total` NEW global ray ids, this rank its shard, one all-reduce"""
+        buf = tr.step_device(total, ray_id0=next_id[0])
+        next_id[0] += total
         return buf
 
+    def timed(total, steps):
+        """(seconds [max over ranks], rays, bounces, launches) of `steps` device-resident steps"""
+        acc = torch.zeros(8, dtype=torch.int64, device=tr.device)
+        barrier()
+        l0 = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            acc += step_dev(total)[nb:nb + 8]
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=tr.device)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        st = acc.cpu().numpy()
+        return ms.item() * 1e-3, int(st[0]), int(st[5]), ctx.launches - l0 + (2 * steps if world > 1 else steps)
+
+    total = args.rays if args.scaling == "strong" else args.rays * world
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     for _ in range(args.warmup):
-        one_step()
+        step_dev(total)
     barrier()
-    l0 = ctx.launches
     t_region0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        buf = one_step()
-        total += buf[nb:nb + 8]
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=tr.device)
-    barrier()
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dt, rays_done, bounces, launches = timed(total, args.steps)
     clk = clocks.stop(t_region0, time.time()) if rank == 0 else None
-    launches = ctx.launches - l0 + (args.steps if world > 1 else 0)   # + the all-reduce kernels
-    dt = ms.item() * 1e-3
-    st = total.cpu().numpy()
-    rays_done, bounces = int(st[0]), int(st[5])
     value = bounces / dt
 
     # ---- e2e: the public blocking call, host results every step (params H2D, map+stats D2H)
@@ -201,8 +260,8 @@ def _run_ours(args):
     t0 = time.perf_counter()
     e2e_bounces = 0
     for _ in range(args.steps):
-        counts, stats = tr.step(world * R, ray_id0=step_no[0] * world * R)
-        step_no[0] += 1
+        counts, stats = tr.step(total, ray_id0=next_id[0])
+        next_id[0] += total
         e2e_bounces += int(stats[0, 5])
     barrier()
     e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=tr.device)
@@ -212,36 +271,56 @@ def _run_ours(args):
     h2d = C.sizeof(A.Scene) + C.sizeof(A.Source) + C.sizeof(A.MapSpec) + 48
     d2h = (nb + 8) * 8
 
-    # ---- per-kernel timing for the roofline (CUDA events inside the library around the trace launches)
-    _, kst = ctx.trace_fluxmap(sc, src, R, mp, seed=4357, ray_id0=step_no[0] * world * R + rank * R)
+    # ---- the other scaling mode, a few steps (N = 1: the same job)
+    other = None
+    if world > 1 and not args.no_other:
+        o_total = args.rays * world if args.scaling == "strong" else args.rays
+        o_steps = min(args.steps, 3)
+        step_dev(o_total)
+        o_dt, o_rays, o_b, _ = timed(o_total, o_steps)
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "value": o_b / o_dt, "unit": UNIT,
+                 "rays_per_step": o_total, "steps": o_steps, "ms_per_step": o_dt / o_steps * 1e3, "rays_per_s": o_rays / o_dt}
+
+    # ---- map_crc: the all-reduced map + stats of a FIXED probe (ray ids 0 .. 1e7-1): the same bytes at every N
+    c_probe, s_probe = tr.step(PROBE_RAYS, ray_id0=0)
+    map_crc = "%08x" % (zlib.crc32(np.ascontiguousarray(c_probe).tobytes() + np.ascontiguousarray(s_probe[:, :6]).tobytes()) & 0xffffffff)
+
+    # ---- per-kernel timing for the roofline (CUDA events inside the library, on its own stream, around the trace launches)
+    l0 = ctx.launches
+    _, kst = ctx.trace_fluxmap(sc, src, total // world, mp, seed=4357, ray_id0=next_id[0] + rank * (total // world))
+    k_launches = ctx.launches - l0
     kst = kst[0]
     peak = ctx.measure_fp32_peak()
-    n_batches = -(-R // (1 << 28))
+    n_trace = max(1, ctx.trace_launches_last) if hasattr(ctx, "trace_launches_last") else max(1, -(-(total // world) // (1 << 28)))
     achieved = FLOP_PER_BOUNCE * kst["n_bounces"] / kst["t_trace_s"] * 1e-12
     roofline = {"bound": "fp32", "kernel": "k_trace<rough,CustomMirror>", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE 2^28-ray launch of this kernel, from the
-                # `ncu --set full` capture in profiles/r01_ncu_final.md (algorithmic: 2^28 rays x 32 B = 8.590e9 B)
-                "traffic": 9.4184e9, "traffic_unit": "B per 2^28-ray launch (ncu, profiles/r01_ncu_final.md)",
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
                 "peak_source": "FFMA-chain probe measured live on this GPU (MEASURED_PEAKS.json has no FP32 number); "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                "flop_per_bounce": FLOP_PER_BOUNCE, "launches": n_batches,
-                "avg_launch_ms": kst["t_trace_s"] * 1e3 / n_batches, "map_ms_per_launch": kst["t_map_s"] * 1e3 / n_batches,
+                "flop_per_bounce": FLOP_PER_BOUNCE,
+                "flop_per_bounce_note": f"SURVEY 8(d) unit of work; the CustomMirror step itself executes ~{FLOP_PER_BOUNCE_MODEL:.0f} "
+                                        "FP32 flop per bounce (DESIGN.md section 7), not used for `achieved`",
+                "launches": n_trace, "kernel_launches_in_call": k_launches,
+                "avg_launch_ms": kst["t_trace_s"] * 1e3 / n_trace, "map_ms_per_launch": kst["t_map_s"] * 1e3 / n_trace,
                 "bounces_per_s_kernel": kst["n_bounces"] / kst["t_trace_s"],
-                "issue_slots_busy_ncu": 0.823, "active_lanes_ncu": 27.6, "fma_pipe_ncu": 0.54, "alu_pipe_ncu": 0.52,
-                "warp_instructions_per_bounce_ncu": 296,
-                "hbm_bytes_per_bounce_algorithmic": 32.0 * kst["n_rays"] / kst["n_bounces"]}
+                "hbm_bytes_per_bounce_algorithmic": 0.0}
+    prof = profile_reference()
+    if prof:
+        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+        roofline["profile_reference"] = prof
     barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.map),
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.map, world),
             "rays_per_s": rays_done / dt, "bounces_per_ray": bounces / max(rays_done, 1),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk,
+            "gpu_launches": int(launches), "map_crc": map_crc,
+            "map_crc_note": f"CRC-32 of the all-reduced map+stats of ray ids 0..{PROBE_RAYS - 1}; identical at every N",
+            "other_scaling": other, "roofline": roofline, "clocks": clk,
             "reference_recorded": {"value": REF_RECORDED, "unit": UNIT, "note": "BASELINE.md, author's PC, <=4 threads"}}
     if world == 1 and not args.no_cpu:
         try:
@@ -250,14 +329,15 @@ def _run_ours(args):
             O.build()
             osc, osrc = workload_scene(O), O.source()
             omp_ = O.map_spec(mode=O.MAP_DIRECTION if args.map == "direction" else O.MAP_LINE)
-            cores = O.lib().orc_num_threads()
-            sample = args.ref_rays if args.map == "direction" else max(args.ref_rays // 20, 1000)   # LINE is brute force on the CPU
+            cores = host_threads()
+            rate, bpr = cpu_rate_probe(O, osc, osrc, omp_, cores)
+            sample = args.ref_rays if args.ref_rays > 0 else int(min(max(rate * 10.0 / bpr, 2_000), 50_000_000))   # ~10 s
             t0 = time.perf_counter()
-            _, ost = O.fluxmap(osc, osrc, sample, omp_, seed=4357, prec=O.F64, n_threads=0)
+            _, ost = O.fluxmap(osc, osrc, sample, omp_, seed=4357, prec=O.F64, n_threads=cores)
             cdt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": ost["n_bounces"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} rays of the same workload, FP64 oracle restatement (ROOT+ROBAST cannot "
-                                              f"run here), {cdt:.1f} s"}
+                                              f"run here), {cdt:.1f} s on {cores} threads"}
             s1 = max(sample // (2 * max(cores, 1)), 1000)          # the same on ONE core, ~half the time again
             t0 = time.perf_counter()
             _, ost1 = O.fluxmap(osc, osrc, s1, omp_, seed=4357, prec=O.F64, n_threads=1)
@@ -274,11 +354,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rays", type=int, default=1_000_000_000, help="rays per GPU per step (C3: 1e9)")
+    ap.add_argument("--rays", type=int, default=C3_RAYS,
+                    help="strong: rays per step of the whole job (C3: 1e9); weak: rays per GPU per step")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--map", choices=["direction", "line"], default="direction")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--ref-rays", type=int, default=20_000_000, help="CPU sample size (rays)")
+    ap.add_argument("--ref-rays", type=int, default=0, help="CPU sample size (rays per step); 0 = sized from a calibration run")
+    ap.add_argument("--ref-budget", type=float, default=90.0, help="seconds the reference arm may spend on its K steps")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary scaling measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
