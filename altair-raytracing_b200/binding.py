@@ -113,6 +113,8 @@ def load_library():
     L.altb_set_batch.argtypes = [vp, u64]
     L.altb_launch_count.argtypes = [vp]
     L.altb_launch_count.restype = u64
+    L.altb_trace_launch_count.argtypes = [vp]
+    L.altb_trace_launch_count.restype = u64
     L.altb_trace_fluxmap.argtypes = [vp, P(Scene), C.c_int, P(Source), u64, u64, u64, P(MapSpec), vp, P(Stats)]
     L.altb_trace_fluxmap_dev.argtypes = [vp, P(Scene), C.c_int, P(Source), u64, u64, u64, P(MapSpec), vp, vp, vp]
     L.altb_trace_exit_rays.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, vp, vp, vp, vp, P(Stats)]
@@ -171,6 +173,10 @@ class Context:
     @property
     def launches(self):
         return int(self._L.altb_launch_count(self._h))
+
+    @property
+    def trace_launches(self):
+        return int(self._L.altb_trace_launch_count(self._h))
 
     def set_batch(self, batch_rays):
         self._check(self._L.altb_set_batch(self._h, int(batch_rays)))

@@ -40,6 +40,12 @@ struct DevCtx {
     // them, so that the tail of one persistent launch (its last long rays) overlaps the start of the next one
     altb_record* rec2 = nullptr; uint64_t rec2_cap = 0;
     unsigned int* counter2 = nullptr;
+    QEntry* rq[2] = {nullptr, nullptr};                 // k_trace's resume queues (one set per launch in flight)
+    unsigned long long* gstat[2] = {nullptr, nullptr};  // k_trace's per-block statistics (direction sink), same
+    unsigned long long* stats_scratch = nullptr; uint64_t stats_scratch_cap = 0;
+    // LINE-map tables of the last map spec (setup_map)
+    bool map_cached = false; altb_map_spec map_key; MapParams map_M; int map_n_tiles = 0; size_t map_line_smem = 0;
+    std::vector<float> tab_host; std::vector<float4> tiles_host;
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -48,7 +54,9 @@ struct DevCtx {
 struct altb_ctx {
     std::vector<DevCtx> devs;
     uint64_t batch = DEFAULT_BATCH;
+    bool batch_user = false;          // altb_set_batch was called: the direction sink honours it too (default there: 2^31)
     uint64_t launches = 0;
+    uint64_t trace_launches = 0;      // k_trace launches only (roofline: average launch duration)
 };
 
 // ---------------------------------------------------------------------------------- scene setup
@@ -124,7 +132,7 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.sincos);
-        cudaFree(d.rec2); cudaFree(d.counter2);
+        cudaFree(d.rec2); cudaFree(d.counter2); cudaFree(d.rq[0]); cudaFree(d.rq[1]); cudaFree(d.gstat[0]); cudaFree(d.gstat[1]); cudaFree(d.stats_scratch);
         for (auto& a : d.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
         if (d.fork_ev) cudaEventDestroy(d.fork_ev);
         for (auto& e : d.join_ev) if (e) cudaEventDestroy(e);
@@ -153,7 +161,9 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         const int dev = devices ? devices[i] : i;
         if (dev < 0 || dev >= avail) { altb_destroy(ctx); return fail(ALTB_E_ARG, "altb_create: bad device %d", dev); }
         cudaDeviceProp prop;
-        if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
+        if (cudaSetDevice(dev) != cudaSuccess) { altb_destroy(ctx); return fail(ALTB_E_CUDA, "altb_create: cudaSetDevice(%d) failed", dev); }
+        d.dev = dev;        // from here on altb_destroy frees whatever this device already owns
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaMalloc(&d.counter2, sizeof(unsigned int)) != cudaSuccess ||
@@ -163,12 +173,15 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
             cudaEventCreateWithFlags(&d.join_ev[0], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&d.join_ev[1], cudaEventDisableTiming) != cudaSuccess ||
             cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.rq[0], (size_t)prop.multiProcessorCount * TRACE_WARPS * RQCAP * sizeof(QEntry)) != cudaSuccess ||
+            cudaMalloc(&d.rq[1], (size_t)prop.multiProcessorCount * TRACE_WARPS * RQCAP * sizeof(QEntry)) != cudaSuccess ||
+            cudaMalloc(&d.gstat[0], (size_t)prop.multiProcessorCount * MAX_SLOTS * STAT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.gstat[1], (size_t)prop.multiProcessorCount * MAX_SLOTS * STAT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&d.sincos, TABS_BYTES) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
             altb_destroy(ctx);
             return fail(ALTB_E_CUDA, "altb_create: device %d init failed: %s", dev, msg);
         }
-        d.dev = dev;
         d.sm_count = prop.multiProcessorCount;
         k_make_sincos_table<<<SC_N / 256, 256, 0, d.stream>>>(d.sincos);
         ctx->launches++;
@@ -188,11 +201,13 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
 extern "C" int altb_set_batch(altb_ctx* ctx, uint64_t batch_rays) {
     if (!ctx) return fail(ALTB_E_ARG, "ctx is NULL");
     ctx->batch = batch_rays ? batch_rays : DEFAULT_BATCH;
-    if (ctx->batch > (1ull << 31)) ctx->batch = 1ull << 31;
+    ctx->batch_user = batch_rays != 0;
+    if (ctx->batch > (1ull << 31) - 1) ctx->batch = (1ull << 31) - 1;   // lane indices are 31 bits in the single-scene instances
     return 0;
 }
 
 extern "C" uint64_t altb_launch_count(const altb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t altb_trace_launch_count(const altb_ctx* ctx) { return ctx ? ctx->trace_launches : 0; }
 
 template <typename T>
 static int ensure(T*& p, uint64_t& cap, uint64_t need) {
@@ -208,6 +223,7 @@ static int ensure(T*& p, uint64_t& cap, uint64_t need) {
 struct TraceSetup { TraceParams P; bool rough; int model; };
 
 static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t seed, TraceSetup& ts) {
+    memset(&ts.P, 0, sizeof ts.P);
     if (int rc = make_geom(sc, ts.P.g, ts.P.k)) return rc;
     const int kind0 = launch_ray(ts.P.g, src->pos, src->dir, ts.P.d0, ts.P.x0);
     if (kind0 < 0) return fail(ALTB_E_SOURCE, "source must lie strictly inside the inner sphere with a non-zero direction");
@@ -216,74 +232,124 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
     ts.P.keys = philox_expand(seed);
     ts.rough = sc->roughness_rad != 0.0;
     ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : (sc->brdf_kind == 2 ? 3 : 0));
+    // one slot: this scene
+    ts.P.n_slots = 1;
+    ts.P.slots[0].zc = ts.P.g.zc; ts.P.slots[0].T2 = ts.P.g.T2; ts.P.slots[0].cth = ts.P.g.cth; ts.P.slots[0].sth = ts.P.g.sth;
+    ts.P.slots[0].zcf = ts.P.k.zc; ts.P.slots[0].scene = 0;
     return 0;
 }
 
-template <bool R, int M>
+// Can scene b ride in the same launch as scene a?  Everything but theta_max must agree: what the hot loop reads
+// (KConsts except zc), the common Geom fields, the first event of the source rays and the kernel instance.
+static bool same_launch(const TraceSetup& a, const TraceSetup& b) {
+    KConsts ka = a.P.k, kb = b.P.k;
+    ka.zc = kb.zc = 0.f;
+    const Geom &ga = a.P.g, &gb = b.P.g;
+    return a.rough == b.rough && a.model == b.model && a.P.kind0 == EV_WALL && b.P.kind0 == EV_WALL &&
+           memcmp(&ka, &kb, sizeof ka) == 0 && ga.R1 == gb.R1 && ga.R2 == gb.R2 && ga.H == gb.H && ga.exit_z == gb.exit_z &&
+           ga.lambertian == gb.lambertian && ga.brdf_kind == gb.brdf_kind && ga.max_bounces == gb.max_bounces &&
+           ga.count_all == gb.count_all && memcmp(a.P.x0f, b.P.x0f, sizeof a.P.x0f) == 0 && memcmp(a.P.d0f, b.P.d0f, sizeof a.P.d0f) == 0 &&
+           memcmp(&a.P.keys, &b.P.keys, sizeof a.P.keys) == 0;
+}
+
+template <bool R, int M, int S>
 static cudaError_t launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
     static thread_local int attr_dev = -1;      // the opt-in to >48 kB of dynamic shared memory is per device and per kernel
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_trace<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_trace<R, M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
         if (e != cudaSuccess) return e;
         attr_dev = dev;
     }
-    if (P.kind0 != EV_WALL) {   // source aimed at the port rim: generic tracer (k_trace's fresh rays start on the sphere)
-        k_trace_generic<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, rec);
-        return cudaGetLastError();
-    }
-    k_trace<R, M><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
+    k_trace<R, M, S><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
     return cudaGetLastError();
 }
 
-// trace rays [ray_id0, ray_id0+n) into d.rec[0..n)
-static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, uint64_t ray_id0, uint32_t n, cudaStream_t st) {
+template <bool R, int M>
+static cudaError_t launch_generic_t(const TraceParams& P, altb_record* rec, cudaStream_t st) {
+    k_trace_generic<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, rec);
+    return cudaGetLastError();
+}
+
+// Trace rays [ray_id0, ray_id0+n) of every slot of ts.P.  sink == SINK_RECORDS: into rec[slot * n + i];
+// SINK_DIRECTION: into P.counts_base / P.stats_base (set by the caller).  The caller keeps [ray_id0, ray_id0+n) inside one
+// 2^32-aligned window of ray ids (pieces()), so that the high counter word is uniform.
+static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_t ray_id0, uint32_t n, altb_record* rec,
+                     unsigned int* counter, QEntry* rq, unsigned long long* gstat, cudaStream_t st) {
     if (n == 0) return 0;
-    if (ts.P.kind0 == EV_EXIT) {   // the source points straight out of the port: every ray is the same record
+    TraceParams& P = ts.P;
+    if (P.kind0 == EV_EXIT) {   // the source points straight out of the port: every ray is the same record
         altb_record proto;
-        for (int i = 0; i < 3; i++) { proto.pos[i] = (float)ts.P.x0[i]; proto.dir[i] = (float)ts.P.d0[i]; }
+        for (int i = 0; i < 3; i++) { proto.pos[i] = (float)P.x0[i]; proto.dir[i] = (float)P.d0[i]; }
         proto.n_hits = 0; proto.status = ALTB_EXITED;
-        k_fill_records<<<d.sm_count * 4, 256, 0, st>>>(d.rec, n, proto);
+        if (sink == SINK_DIRECTION)
+            k_all_exit_direction<<<1, 32, 0, st>>>(proto, n, P.n_theta, P.n_phi, P.k.exit_zf, P.counts_base + (size_t)P.slots[0].scene * P.nb,
+                                                   P.stats_base + (size_t)P.slots[0].scene * 8);
+        else k_fill_records<<<d.sm_count * 4, 256, 0, st>>>(rec, n, proto);
         ctx->launches++;
         CK(cudaGetLastError());
         return 0;
     }
-    TraceParams& P = ts.P;
-    P.ray_id0 = ray_id0; P.n = n;
-    P.sincos = d.sincos;
+    P.ray_id0 = ray_id0; P.ctr_lo0 = (uint32_t)ray_id0; P.ctr_hi = (uint32_t)(ray_id0 >> 32);
+    P.n = n;
+    P.sincos = d.sincos; P.rq = rq; P.gstat = gstat;
+    uint32_t sbits = 1;
+    while ((1u << sbits) < P.n_slots) sbits++;
+    P.shift = 32 - sbits; P.imask = (1u << P.shift) - 1u;
+    if ((uint64_t)n >= (1ull << P.shift)) return fail(ALTB_E_ARG, "run_trace: %u rays x %u slots do not fit one launch", n, P.n_slots);
+    if (P.n_slots > 1 && sink != SINK_DIRECTION) return fail(ALTB_E_ARG, "run_trace: batched scenes need the direction sink");
+    const uint64_t total = (uint64_t)n * P.n_slots;
     int blocks = d.sm_count;                           // persistent: one 1024-thread block per SM
-    const uint32_t warps_needed = (n + 31) / 32;
-    if ((uint32_t)blocks * TRACE_WARPS > warps_needed) blocks = (int)((warps_needed + TRACE_WARPS - 1) / TRACE_WARPS);
+    const uint64_t warps_needed = (total + 31) / 32;
+    if ((uint64_t)blocks * TRACE_WARPS > warps_needed) blocks = (int)((warps_needed + TRACE_WARPS - 1) / TRACE_WARPS);
     // ids are claimed in chunks; small enough that the tail (last chunk per warp) stays short
     uint32_t chunk = 256;
-    while (chunk > 32 && (uint64_t)chunk * blocks * TRACE_WARPS * 4 > n) chunk >>= 1;
+    while (chunk > 32 && (uint64_t)chunk * blocks * TRACE_WARPS * 4 > total) chunk >>= 1;
     if (const char* e = getenv("ALTB_CHUNK")) { const long v = atol(e); if (v >= 32 && v <= 65536) chunk = (uint32_t)v; }   // tuning knob
     P.chunk = chunk;
-    CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
+    P.cps = (n + chunk - 1) / chunk;
+    P.n_chunks = P.cps * P.n_slots;
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (sink == SINK_DIRECTION) CK(cudaMemsetAsync(gstat, 0, (size_t)blocks * P.n_slots * STAT_WORDS * sizeof(unsigned long long), st));
     cudaError_t le = cudaSuccess;
-    if (ts.rough) {
-        if (ts.model == 0) le = launch_trace_t<true, 0>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 1) le = launch_trace_t<true, 1>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 2) le = launch_trace_t<true, 2>(P, d.rec, d.counter, blocks, st);
-        else le = launch_trace_t<true, 3>(P, d.rec, d.counter, blocks, st);
+    if (P.kind0 != EV_WALL) {   // source aimed at the port rim: generic tracer (k_trace's fresh rays start on the sphere)
+        if (sink != SINK_RECORDS || P.n_slots != 1) return fail(ALTB_E_ARG, "run_trace: rim-aimed sources go through the record path");
+#define GEN(RR, MM) le = launch_generic_t<RR, MM>(P, rec, st)
+        if (ts.rough) { if (ts.model == 0) GEN(true, 0); else if (ts.model == 1) GEN(true, 1); else if (ts.model == 2) GEN(true, 2); else GEN(true, 3); }
+        else          { if (ts.model == 0) GEN(false, 0); else if (ts.model == 1) GEN(false, 1); else if (ts.model == 2) GEN(false, 2); else GEN(false, 3); }
+#undef GEN
     } else {
-        if (ts.model == 0) le = launch_trace_t<false, 0>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 1) le = launch_trace_t<false, 1>(P, d.rec, d.counter, blocks, st);
-        else if (ts.model == 2) le = launch_trace_t<false, 2>(P, d.rec, d.counter, blocks, st);
-        else le = launch_trace_t<false, 3>(P, d.rec, d.counter, blocks, st);
+#define GO(RR, MM) le = (sink != SINK_DIRECTION ? launch_trace_t<RR, MM, SINK_RECORDS>(P, rec, counter, blocks, st) \
+                         : P.n_slots > 1 ? launch_trace_t<RR, MM, SINK_DIRECTION_BATCHED>(P, rec, counter, blocks, st) \
+                                         : launch_trace_t<RR, MM, SINK_DIRECTION>(P, rec, counter, blocks, st))
+        if (ts.rough) { if (ts.model == 0) GO(true, 0); else if (ts.model == 1) GO(true, 1); else if (ts.model == 2) GO(true, 2); else GO(true, 3); }
+        else          { if (ts.model == 0) GO(false, 0); else if (ts.model == 1) GO(false, 1); else if (ts.model == 2) GO(false, 2); else GO(false, 3); }
+#undef GO
     }
     ctx->launches++;
+    ctx->trace_launches++;
     CK(le);
+    if (sink == SINK_DIRECTION) {
+        k_reduce_trace_stats<<<(P.n_slots * STAT_WORDS + 127) / 128, 128, 0, st>>>(P, blocks);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
+}
+
+// [off, off+len) pieces of a ray-id range: at most `cap` rays each, none straddling a multiple of 2^32 of the GLOBAL id
+static inline uint64_t piece_len(uint64_t ray_id, uint64_t left, uint64_t cap) {
+    const uint64_t to_wrap = (1ull << 32) - (ray_id & 0xffffffffull);
+    return std::min(std::min(left, cap), to_wrap);
 }
 
 // ---------------------------------------------------------------------------------- map setup
 struct MapSetup { MapParams M; int n_tiles; size_t line_smem; size_t dir_smem; };
 
-static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KConsts& k, const altb_map_spec* map,
+static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom& g, const KConsts& k, const altb_map_spec* map,
                      MapSetup& ms, cudaStream_t st) {
-    (void)sc;
+    (void)sc; (void)ctx;
     if (map->n_theta < 1 || map->n_phi < 1 || (int64_t)map->n_theta * map->n_phi > (1 << 24))
         return fail(ALTB_E_ARG, "map: bad bin counts %d x %d", map->n_theta, map->n_phi);
     if (map->map_mode < ALTB_MAP_LINE || map->map_mode > ALTB_MAP_TWOFOLD) return fail(ALTB_E_ARG, "map: bad map_mode %d", map->map_mode);
@@ -305,8 +371,20 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     (void)grouped;
     if (!(map->det_radius > 0) || !(map->det_width > 0)) return fail(ALTB_E_ARG, "map: det_radius/det_width must be > 0");
 
+    // The tables depend on the map spec only: a context that keeps mapping with the same spec (every step of a run, every
+    // scene of a sweep) builds and uploads them once.
+    if (d.map_cached && d.map_key.n_theta == nt && d.map_key.n_phi == np && d.map_key.det_radius == map->det_radius &&
+        d.map_key.det_width == map->det_width) {
+        M.t_theta = d.map_M.t_theta; M.t_phi = d.map_M.t_phi; M.nt_theta = d.map_M.nt_theta; M.nt_phi = d.map_M.nt_phi;
+        M.rs = d.map_M.rs; M.pz = d.map_M.pz; M.st = d.map_M.st; M.ct = d.map_M.ct; M.cp = d.map_M.cp; M.sp = d.map_M.sp;
+        M.tiles = d.map_M.tiles; M.supers = d.map_M.supers;
+        ms.n_tiles = d.map_n_tiles; ms.line_smem = d.map_line_smem;
+        return 0;
+    }
+    if (d.map_cached) { CK(cudaDeviceSynchronize()); d.map_cached = false; }     // kernels of an earlier call may still read the old tables
     // per-row / per-column tables (Detector::setPosition, fluxAtObserverFast.C:61-80), rounded once to f32
-    std::vector<float> tab((size_t)4 * nt + 2 * np);
+    std::vector<float>& tab = d.tab_host;
+    tab.assign((size_t)4 * nt + 2 * np, 0.f);
     std::vector<double> px((size_t)nt * np), py((size_t)nt * np), pzv((size_t)nt * np);
     for (int i = 0; i < nt; i++) {
         const double th = (i + 0.5) * 90.0 / nt * PI_D / 180.0;
@@ -329,7 +407,8 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     // tile shape: the (t_theta x t_phi) <= 32 bins with the smallest mean bounding radius
     const int shapes[6][2] = {{32, 1}, {16, 2}, {8, 4}, {4, 8}, {2, 16}, {1, 32}};
     double best = 1e300; int bt = 8, bp = 4;
-    std::vector<float4> best_tiles;
+    std::vector<float4>& best_tiles = d.tiles_host;     // staging lives in the context: nothing to wait for after the uploads
+    best_tiles.clear();
     auto bound = [&](int i0, int i1, int j0, int j1) {     // bounding sphere of the detector centres of bins [i0,i1) x [j0,j1)
         double cx = 0, cy = 0, cz = 0; int cnt = 0;
         for (int i = i0; i < i1; i++)
@@ -385,16 +464,16 @@ static int setup_map(DevCtx& d, const altb_scene* sc, const Geom& g, const KCons
     if (int rc = ensure(d.tiles, d.tiles_cap, (uint64_t)best_tiles.size())) return rc;
     CK(cudaMemcpyAsync(d.tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d.tiles, best_tiles.data(), best_tiles.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));   // the host vectors die at return
     M.rs = d.tables; M.pz = d.tables + nt; M.st = d.tables + 2 * nt; M.ct = d.tables + 3 * nt;
     M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
     M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
+    d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_cached = true;
     return 0;
 }
 
 // records d.rec[0..n) -> counts (+stats)
-static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uint64_t ray_base, unsigned long long* d_counts,
-                   unsigned long long* d_stats, int* d_bin, cudaStream_t st) {
+static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const altb_record* rec, unsigned int* counter, uint32_t n, uint64_t ray_base,
+                   unsigned long long* d_counts, unsigned long long* d_stats, int* d_bin, cudaStream_t st) {
     if (n == 0) return 0;
     const MapParams& M = ms.M;
     if (M.mode == ALTB_MAP_DIRECTION) {
@@ -405,7 +484,7 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
         int blocks = d.sm_count * (per_sm < 1 ? 1 : per_sm);
         const int need = (int)((n + DIR_THREADS - 1) / DIR_THREADS);
         if (blocks > need) blocks = need;
-        k_map_direction<<<blocks, DIR_THREADS, ms.dir_smem, st>>>(d.rec, n, M, d_counts, d_stats, d_bin);
+        k_map_direction<<<blocks, DIR_THREADS, ms.dir_smem, st>>>(rec, n, M, d_counts, d_stats, d_bin);
         ctx->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -414,7 +493,7 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
         int blocks = d.sm_count * 4;
         const int need = (int)((n + 255) / 256);
         if (blocks > need) blocks = need;
-        k_stats<<<blocks, 256, 0, st>>>(d.rec, n, M.count_all, M.exit_zf, d_stats);
+        k_stats<<<blocks, 256, 0, st>>>(rec, n, M.count_all, M.exit_zf, d_stats);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -422,19 +501,19 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
         int blocks = d.sm_count * 8;
         const int need = (int)((n + 255) / 256);
         if (blocks > need) blocks = need;
-        k_map_per_position<<<blocks, 256, 0, st>>>(d.rec, n, M, (unsigned long long)ray_base, d_counts);
+        k_map_per_position<<<blocks, 256, 0, st>>>(rec, n, M, (unsigned long long)ray_base, d_counts);
         ctx->launches++;
         CK(cudaGetLastError());
         return 0;
     }
     CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;
-    CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     {
         int cb = d.sm_count * 8;
         const int need = (int)((n + 255) / 256);
         if (cb > need) cb = need;
-        k_compact_exits<<<cb, 256, 0, st>>>(d.rec, n, M, d.lines, d.counter);
+        k_compact_exits<<<cb, 256, 0, st>>>(rec, n, M, d.lines, counter);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -444,71 +523,113 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, uint32_t n, uin
     int blocks = d.sm_count * per_sm;
     const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
     if (blocks > need) blocks = need;
-    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.lines, d.counter, M, d_counts);
+    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.lines, counter, M, d_counts);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------- hot path
+// One launch slot of a job: stream, chunk counter, resume queues and (record sink) the record buffer.  Jobs with several
+// launches and no per-kernel timing alternate between two slots on two worker streams forked from / joined to the caller's
+// stream, so that the tail of one persistent launch (its last long rays) overlaps the start of the next one.
+struct LaunchSlot { cudaStream_t st; unsigned int* counter; QEntry* rq; unsigned long long* gstat; altb_record* rec; };
+
 static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes, int n_scenes, const altb_source* src,
                              uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
                              unsigned long long* d_counts, unsigned long long* d_stats, cudaStream_t st,
                              float* t_trace_ms, float* t_map_ms) {
     CK(cudaSetDevice(d.dev));
     const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
-    const uint64_t batch = std::min<uint64_t>(ctx->batch, std::max<uint64_t>(n_rays, 1));
-    if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
-    // Two launches in flight (see DevCtx): only where nothing but the records and the counter are per-launch state
-    // (DIRECTION maps) and nobody asked for per-kernel timings.
-    const uint64_t n_launches = (uint64_t)n_scenes * ((n_rays + batch - 1) / batch);
-    const bool overlap = !t_trace_ms && map->map_mode == ALTB_MAP_DIRECTION && n_launches >= 2 && !getenv("ALTB_NO_OVERLAP");
-    if (overlap) {
-        if (int rc = ensure(d.rec2, d.rec2_cap, batch)) return rc;
-        CK(cudaEventRecord(d.fork_ev, st));
-        CK(cudaStreamWaitEvent(d.aux[0], d.fork_ev, 0));
-        CK(cudaStreamWaitEvent(d.aux[1], d.fork_ev, 0));
+    if (n_rays == 0) return 0;
+    std::vector<TraceSetup> tss((size_t)n_scenes);
+    for (int s = 0; s < n_scenes; s++)
+        if (int rc = setup_trace(&scenes[s], src, seed, tss[s])) return rc;
+    MapSetup ms;                                         // tables depend on the map spec only; count_all / exit_z are patched per scene
+    if (int rc = setup_map(ctx, d, &scenes[0], tss[0].P.g, tss[0].P.k, map, ms, st)) return rc;
+    if (!d_stats) {                                      // the direction sink always keeps statistics
+        if (int rc = ensure(d.stats_scratch, d.stats_scratch_cap, (uint64_t)n_scenes * 8)) return rc;
+        d_stats = d.stats_scratch;
     }
-    altb_record* const rec_main = d.rec;
-    unsigned int* const counter_main = d.counter;
+    // ---- plan: which scenes share launches
+    const bool dir_mode = map->map_mode == ALTB_MAP_DIRECTION;
+    auto dir_sink_ok = [&](int s) { return dir_mode && !tss[s].P.g.count_all && (tss[s].P.kind0 == EV_WALL || tss[s].P.kind0 == EV_EXIT); };
+    std::vector<std::vector<int>> groups;
+    std::vector<char> seen((size_t)n_scenes, 0);
+    for (int s = 0; s < n_scenes; s++) {
+        if (seen[s]) continue;
+        seen[s] = 1;
+        groups.push_back({s});
+        if (!dir_sink_ok(s) || tss[s].P.kind0 != EV_WALL || getenv("ALTB_NO_BATCH")) continue;
+        for (int t = s + 1; t < n_scenes && (int)groups.back().size() < MAX_SLOTS; t++)
+            if (!seen[t] && dir_sink_ok(t) && same_launch(tss[s], tss[t])) { seen[t] = 1; groups.back().push_back(t); }
+    }
+    // ---- launches of the whole job, to decide about the overlap
+    const uint64_t batch_rec = std::min<uint64_t>(std::min<uint64_t>(ctx->batch, (1ull << 31) - 1), n_rays);
+    auto dir_cap = [&](size_t G) -> uint64_t {          // rays per slot of one direction-sink launch of G slots
+        uint32_t sbits = 1;
+        while ((1u << sbits) < G) sbits++;
+        const uint64_t total = ctx->batch_user ? ctx->batch : 0xfff00000ull;      // dense work index < 2^32
+        return std::max<uint64_t>(1, std::min<uint64_t>(total / G, (1ull << (32 - sbits)) - 1));
+    };
+    uint64_t n_launches = 0;
+    bool any_rec = false;
+    for (auto& g : groups) {
+        const bool dsink = dir_sink_ok(g[0]);
+        const uint64_t cap = dsink ? dir_cap(g.size()) : batch_rec;
+        n_launches += (n_rays + cap - 1) / cap;
+        any_rec |= !dsink;
+    }
+    if (any_rec) if (int rc = ensure(d.rec, d.rec_cap, batch_rec)) return rc;
+    const bool overlap = !t_trace_ms && dir_mode && n_launches >= 2 && !getenv("ALTB_NO_OVERLAP");
+    LaunchSlot ls[2] = {{st, d.counter, d.rq[0], d.gstat[0], d.rec}, {st, d.counter2, d.rq[1], d.gstat[1], d.rec}};
+    if (overlap) {
+        if (any_rec) { if (int rc = ensure(d.rec2, d.rec2_cap, batch_rec)) return rc; ls[1].rec = d.rec2; }
+        CK(cudaEventRecord(d.fork_ev, st));
+        for (int i = 0; i < 2; i++) { CK(cudaStreamWaitEvent(d.aux[i], d.fork_ev, 0)); ls[i].st = d.aux[i]; }
+    }
     uint64_t launch_no = 0;
     int rc_all = 0;
-    for (int s = 0; s < n_scenes && !rc_all; s++) {
-        TraceSetup ts;
-        if ((rc_all = setup_trace(&scenes[s], src, seed, ts))) break;
-        MapSetup ms;
-        if ((rc_all = setup_map(d, &scenes[s], ts.P.g, ts.P.k, map, ms, st))) break;
+    for (size_t gi = 0; gi < groups.size() && !rc_all; gi++) {
+        const std::vector<int>& g = groups[gi];
+        TraceSetup& ts = tss[g[0]];
+        const bool dsink = dir_sink_ok(g[0]);
         float tt = 0.f, tm = 0.f;
-        for (uint64_t off = 0; off < n_rays && !rc_all; off += batch, launch_no++) {
-            const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
-            cudaStream_t ls = st;
-            if (overlap) {                              // run_trace / run_map read the buffers from the context
-                const int slot = (int)(launch_no & 1);
-                ls = d.aux[slot];
-                d.rec = slot ? d.rec2 : rec_main;
-                d.counter = slot ? d.counter2 : counter_main;
-            }
-            if (t_trace_ms) CK(cudaEventRecord(d.ev[0], ls));
-            rc_all = run_trace(ctx, d, ts, ray_id0 + off, n, ls);
-            if (!rc_all && t_trace_ms) CK(cudaEventRecord(d.ev[1], ls));
-            if (!rc_all)
-                rc_all = run_map(ctx, d, ms, n, ray_id0 + off, d_counts + (size_t)s * nb, d_stats ? d_stats + (size_t)s * 8 : nullptr, nullptr, ls);
-            d.rec = rec_main; d.counter = counter_main;
+        if (dsink) {
+            ts.P.n_slots = (uint32_t)g.size();
+            for (size_t j = 0; j < g.size(); j++) { ts.P.slots[j] = tss[g[j]].P.slots[0]; ts.P.slots[j].scene = (uint32_t)g[j]; }
+            ts.P.counts_base = d_counts; ts.P.stats_base = d_stats;
+            ts.P.nb = (uint32_t)nb; ts.P.n_theta = map->n_theta; ts.P.n_phi = map->n_phi;
+        }
+        const uint64_t cap = dsink ? dir_cap(g.size()) : batch_rec;
+        MapSetup msg = ms;
+        msg.M.count_all = ts.P.g.count_all; msg.M.exit_zf = ts.P.k.exit_zf;
+        for (uint64_t off = 0; off < n_rays && !rc_all; launch_no++) {
+            const uint32_t n = (uint32_t)piece_len(ray_id0 + off, n_rays - off, cap);
+            const LaunchSlot& L = ls[overlap ? (launch_no & 1) : 0];
+            if (t_trace_ms) CK(cudaEventRecord(d.ev[0], L.st));
+            rc_all = run_trace(ctx, d, ts, dsink ? SINK_DIRECTION : SINK_RECORDS, ray_id0 + off, n, L.rec, L.counter, L.rq, L.gstat, L.st);
+            if (!rc_all && t_trace_ms) CK(cudaEventRecord(d.ev[1], L.st));
+            if (!rc_all && !dsink)
+                rc_all = run_map(ctx, d, msg, L.rec, L.counter, n, ray_id0 + off, d_counts + (size_t)g[0] * nb, d_stats + (size_t)g[0] * 8, nullptr, L.st);
             if (!rc_all && t_trace_ms) {
-                CK(cudaEventRecord(d.ev[2], ls));
+                CK(cudaEventRecord(d.ev[2], L.st));
                 CK(cudaEventSynchronize(d.ev[2]));
                 float a = 0.f, b = 0.f;
                 CK(cudaEventElapsedTime(&a, d.ev[0], d.ev[1]));
                 CK(cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
                 tt += a; tm += b;
             }
+            off += n;
         }
-        if (t_trace_ms) { t_trace_ms[s] = tt; t_map_ms[s] = tm; }
+        // scenes that shared launches share their device time equally
+        if (t_trace_ms) for (int sidx : g) { t_trace_ms[sidx] = tt / g.size(); t_map_ms[sidx] = tm / g.size(); }
     }
     if (overlap) {                                      // join, also on the error path
         for (int i = 0; i < 2; i++) {
-            CK(cudaEventRecord(d.join_ev[i], d.aux[i]));
-            CK(cudaStreamWaitEvent(st, d.join_ev[i], 0));
+            cudaError_t e = cudaEventRecord(d.join_ev[i], d.aux[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, d.join_ev[i], 0);
+            if (e != cudaSuccess && !rc_all) rc_all = fail(ALTB_E_CUDA, "fluxmap: stream join failed: %s", cudaGetErrorString(e));
         }
     }
     return rc_all;
@@ -583,9 +704,9 @@ extern "C" int altb_trace_records(altb_ctx* ctx, const altb_scene* scene, const 
     if (int rc = ensure(d.rec, d.rec_cap, batch)) return rc;
     CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
     CK(cudaEventRecord(d.ev[0], d.stream));
-    for (uint64_t off = 0; off < n_rays; off += batch) {
-        const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
-        if (int rc = run_trace(ctx, d, ts, ray_id0 + off, n, d.stream)) return rc;
+    for (uint64_t off = 0, n = 0; off < n_rays; off += n) {
+        n = piece_len(ray_id0 + off, n_rays - off, batch);
+        if (int rc = run_trace(ctx, d, ts, SINK_RECORDS, ray_id0 + off, (uint32_t)n, d.rec, d.counter, d.rq[0], d.gstat[0], d.stream)) return rc;
         if (stats) {
             k_stats<<<d.sm_count * 4, 256, 0, d.stream>>>(d.rec, n, ts.P.g.count_all, ts.P.k.exit_zf, d.stats);
             ctx->launches++;
@@ -642,7 +763,7 @@ extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const al
     Geom g; KConsts k;
     if (int rc = make_geom(scene, g, k)) return rc;
     MapSetup ms;
-    if (int rc = setup_map(d, scene, g, k, map, ms, d.stream)) return rc;
+    if (int rc = setup_map(ctx, d, scene, g, k, map, ms, d.stream)) return rc;
     const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
     if (int rc = ensure(d.counts, d.counts_cap, nb + 8)) return rc;
     CK(cudaMemsetAsync(d.counts, 0, nb * sizeof(unsigned long long), d.stream));
@@ -651,7 +772,7 @@ extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const al
     for (uint64_t off = 0; off < n; off += batch) {
         const uint32_t m = (uint32_t)std::min<uint64_t>(batch, n - off);
         CK(cudaMemcpyAsync(d.rec, records + off, (size_t)m * sizeof(altb_record), cudaMemcpyHostToDevice, d.stream));
-        if (int rc = run_map(ctx, d, ms, m, off, d.counts, nullptr, nullptr, d.stream)) return rc;
+        if (int rc = run_map(ctx, d, ms, d.rec, d.counter, m, off, d.counts, nullptr, nullptr, d.stream)) return rc;
     }
     std::vector<unsigned long long> host(nb);
     CK(cudaMemcpyAsync(host.data(), d.counts, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
@@ -682,9 +803,9 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
             cudaMemcpyAsync(d_geo + (size_t)m * 3, det_rot, (size_t)m * 9 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess ||
             cudaMemsetAsync(d_hits, 0, (size_t)m * sizeof(unsigned long long), d.stream) != cudaSuccess ||
             cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream) != cudaSuccess) { rc = fail(ALTB_E_CUDA, "detector_sweep: upload failed"); break; }
-        for (uint64_t off = 0; off < n_rays && !rc; off += batch) {
-            const uint32_t n = (uint32_t)std::min<uint64_t>(batch, n_rays - off);
-            rc = run_trace(ctx, d, ts, ray_id0 + off, n, d.stream);
+        for (uint64_t off = 0, n = 0; off < n_rays && !rc; off += n) {
+            n = piece_len(ray_id0 + off, n_rays - off, batch);
+            rc = run_trace(ctx, d, ts, SINK_RECORDS, ray_id0 + off, (uint32_t)n, d.rec, d.counter, d.rq[0], d.gstat[0], d.stream);
             if (rc) break;
             k_stats<<<d.sm_count * 4, 256, 0, d.stream>>>(d.rec, n, ts.P.g.count_all, ts.P.k.exit_zf, d.stats);
             int blocks = d.sm_count * 4;
@@ -791,7 +912,7 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
         if (bin && map) {
             MapSetup ms;
             altb_map_spec m2 = *map; m2.map_mode = ALTB_MAP_DIRECTION;
-            rc = setup_map(d, scene, P.g, P.k, &m2, ms, d.stream);
+            rc = setup_map(ctx, d, scene, P.g, P.k, &m2, ms, d.stream);
             if (rc) break;
             MapParams M = ms.M; M.use_smem_hist = 0;
             k_map_direction<<<d.sm_count * 2, DIR_THREADS, 0, d.stream>>>(d.rec, (uint32_t)n_rays, M, nullptr, nullptr, d_bin);

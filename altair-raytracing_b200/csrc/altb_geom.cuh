@@ -27,18 +27,40 @@ struct KConsts {
     uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
 };
 
+// Per-scene constants of a batched launch.  The scenes of ONE launch differ only in theta_max (the port-angle series of
+// fluxAtObserverFast.C:1641-1673); everything the hot loop reads from KConsts is common to the launch, the port plane zcf
+// rides along in a per-lane register.  The table travels in the kernel's parameter space (no upload, no lifetime): it is
+// read with indexed constant loads when a warp claims work and in the slow paths.
+struct SceneSlot {
+    double zc, T2, cth, sth;           // Geom fields that depend on theta_max
+    float zcf;                         // (float) zc
+    uint32_t scene;                    // index of the scene in the caller's arrays: counts_base + scene * nb, stats_base + scene * 8
+};
+static constexpr int MAX_SLOTS = 192;
+
+struct QEntry { float4 a, b; };        // a parked ray: pos.xyz, dir.x | dir.yz, idx, hits
+
 struct TraceParams {
-    Geom g;
+    Geom g;               // slot-dependent fields (zc, T2, cth, sth) are those of slot 0; the slow path patches them per ray
     KConsts k;
     int kind0;            // first event of the (identical) source rays
     double x0[3];         // its point
     double d0[3];         // unit source direction
     float x0f[3], d0f[3]; // the same, rounded once (what every fresh ray starts from)
     PhiloxKeys keys;      // round keys of the seed
-    uint64_t ray_id0;     // global id of local ray 0
-    uint32_t n;           // rays in this launch
+    uint64_t ray_id0;     // global id of local ray 0 (the launch never straddles a multiple of 2^32: ctr_hi is uniform)
+    uint32_t ctr_lo0, ctr_hi;   // the same as two counter words
+    uint32_t n;           // rays PER SLOT in this launch
     uint32_t chunk;       // ids a warp claims at a time
+    // batched scenes: lane index idx = slot << shift | i, i < n <= 2^shift; work is claimed in chunks q = slot * cps + c
+    uint32_t n_slots, shift, imask, cps, n_chunks;
+    QEntry* rq;           // resume queues in global memory: [grid * warps][RQCAP]
+    unsigned long long* gstat;   // SINK_DIRECTION: per-block statistics [grid][n_slots][STAT_WORDS], zeroed before the launch
+    // SINK_DIRECTION: the maps / statistics the kernel adds to, bins of the direction map
+    unsigned long long* counts_base; unsigned long long* stats_base;
+    uint32_t nb; int n_theta, n_phi;
     const float2* sincos; // device tables: SC_N sin/cos entries + LG_N log entries (altb_math.cuh: DrawTabs)
+    SceneSlot slots[MAX_SLOTS];
 };
 
 ALTB_HD void box_exit(const Geom& g, const double* x, const double* d, double* e) {

@@ -39,8 +39,9 @@ static constexpr int ST_CROSSING = 100;
 // s.pos = the crossing point and s.dir = the new direction (DEFER_CROSSING only).
 // DEFER_CROSSING is the hot loop of k_trace: the ray is on the inner sphere by construction (s.where is not looked at),
 // everything that involves the port edge happens in the kernel's slow path.
+// zcf = the port plane R1 cos(theta_max) of the ray's scene (k.zc for single-scene launches; per lane in batched ones).
 template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
-__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, const DrawTabs& T, RayState& s, const HitDraws& dr) {
+__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, float zcf, const DrawTabs& T, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
     if (DEFER_CROSSING || s.where == EV_WALL) {
@@ -81,7 +82,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
         f3 x = axpy3(t, d, s.pos);
         x = scale3(fma_(dot3(x, x), k.nr_c, 1.5f), x);
         s.pos = x; s.dir = d;
-        if (x.z >= k.zc) return 0;                                   // fast path: wall to wall
+        if (x.z >= zcf) return 0;                                    // fast path: wall to wall
         if (DEFER_CROSSING) return ST_CROSSING;
         const double xd[3] = {(double)x.x, (double)x.y, (double)x.z};
         const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
@@ -106,9 +107,23 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, cons
 // every fifth iteration): the lane parks (crossing point, direction, id, hits) in the warp's shared-memory
 // queue and moves on; the warp drains the queue 32 entries at a time at full SIMT width.  Crossings that
 // turn out to hit the port edge (4 % of them) bounce there out of line (edge_bounces) and come back through
-// the resume queue once they are on the inner sphere again.
+// the resume queue (global memory: it sees one ray per ~4000 surface hits) once they are on the inner sphere again.
+//
+// BATCHED SCENES (the port-angle series fluxAtObserverFast.C:1641-1673, the sweeps of integratingSphereDetectorSweep.C:54-77):
+// one launch traces the same ray ids through n_slots scenes that differ only in theta_max.  The lane's ray index is
+// idx = slot << shift | i; work is claimed in chunks that never straddle a slot; the only per-scene quantity of the hot
+// loop, the port plane zcf, lives in a per-lane register; the slow path patches the slot's Geom fields in.  One kernel
+// tail per sweep instead of one per scene.  Single-scene launches use the non-batched instances (idx = i, port plane
+// straight from the constant bank: the extra live register costs spills at 64 registers per thread).
+//
+// SINK: where a finished ray goes.
+//   SINK_RECORDS    the 32-byte record rec[slot * n + i] (LINE maps, per-ray results, detector sweeps);
+//   SINK_DIRECTION  nowhere: the escaping ray is binned by exit direction right in the slow path (one global
+//                   RED.64 per escaping ray into its scene's map) and the statistics are kept in per-block
+//                   shared-memory counters (shared atomics at the ray's end, one flush per block): no record round trip,
+//                   no map kernel.  Host rule: only for scenes with count_all_status == 0.
 // One 1024-thread block per SM (64 registers per thread): its shared memory holds the draw tables (64 kB
-// sin/cos + 2 kB log, altb_math.cuh: DrawTabs) and the two queues of each of its 32 warps.
+// sin/cos + 2 kB log, altb_math.cuh: DrawTabs), the crossing queue of each of its 32 warps and the statistics counters.
 #ifndef ALTB_TRACE_THREADS
 #define ALTB_TRACE_THREADS 1024
 #endif
@@ -124,34 +139,130 @@ static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 // 32 crossings and the drain leaves fewer than 32 behind: nx <= 31 + 32.  Resumed rays are taken back before fresh ids
 // and every crossing frees a lane, so the resume queue holds at most the crossing backlog plus one pass: nr <= 63 + 32.
 static constexpr int XQCAP = 64, RQCAP = 96;
+enum { SINK_RECORDS = 0, SINK_DIRECTION = 1, SINK_DIRECTION_BATCHED = 2 };   // BATCHED: several slots (per-lane port plane)
+// per-slot statistics words of a block (SINK_DIRECTION): exited, through the port, absorbed, suspended, bounces.
+// They live in GLOBAL memory, private to the block (P.gstat[block][slot][STAT_WORDS], zeroed before the launch, summed into
+// the scenes' statistics by k_reduce_trace_stats after it): a finished ray costs two RED.64 (no return value, nothing
+// waits for them) on addresses no other SM touches.  Kept out of shared memory and out of the kernel's epilogue on
+// purpose: a flush of shared counters at the end of k_trace, inlined or not, made ptxas spill the ray state inside the
+// bounce bodies (40 local-memory instructions per 3 bounces).
+static constexpr int STAT_WORDS = 5;
 
-extern __shared__ __align__(16) unsigned char trace_smem[];     // k_trace: draw tables, then the warps' queues
+extern __shared__ __align__(16) unsigned char trace_smem[];     // k_trace: draw tables, crossing queues
+
+static constexpr size_t TRACE_SMEM = TABS_BYTES + (size_t)TRACE_WARPS * XQCAP * sizeof(QEntry);
+
+__device__ __forceinline__ unsigned long long* trace_stats(const TraceParams& P, uint32_t n_slots, uint32_t slot) {
+    return P.gstat + ((size_t)blockIdx.x * n_slots + slot) * STAT_WORDS;
+}
+__device__ __forceinline__ void stat_end(unsigned long long* gs, int word, uint32_t hits) {
+    atomicAdd(gs + word, 1ull);
+    atomicAdd(gs + 4, (unsigned long long)hits);
+}
+
+// Geom of the ray's scene: the launch's common fields + the slot's theta_max fields
+__device__ __forceinline__ void slot_geom(const TraceParams& P, uint32_t slot, Geom& g) {
+    g = P.g;
+    const SceneSlot* sl = P.slots + slot;       // indexed constant loads (kernel parameter space)
+    g.zc = sl->zc; g.T2 = sl->T2; g.cth = sl->cth; g.sth = sl->sth;
+}
+
+__device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const f3& d);
+
+// SINK_DIRECTION: an exited ray (world-box point pos, direction dir).  Out of line: double-precision acos / atan2 must not
+// cost the hot loop any registers.
+__device__ __noinline__ void exit_to_map(const TraceParams& P, uint32_t slot, float pos_z, float dx, float dy, float dz, uint32_t hits) {
+    unsigned long long* gs = trace_stats(P, P.n_slots, slot);
+    stat_end(gs, 0, hits);
+    if (pos_z < P.k.exit_zf) {
+        atomicAdd(gs + 1, 1ull);
+        const f3 d = {dx, dy, dz};
+        const int b = direction_bin(P.n_theta, P.n_phi, d);
+        if (b >= 0) atomicAdd(P.counts_base + (size_t)P.slots[slot].scene * P.nb + b, 1ull);
+    }
+}
 
 // A ray on the port edge: bounce with the generic step until it is back on the inner sphere (returns 0) or ends
 // (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
 // loop any registers.
 template <bool ROUGH, int MODEL>
-__device__ __noinline__ int edge_bounces(const TraceParams& P, const DrawTabs& T, uint32_t id, RayState& t) {
+__device__ __noinline__ int edge_bounces(const TraceParams& P, const Geom& g, const DrawTabs& T, uint32_t ctr_lo, RayState& t) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;     // (T by reference: rebuilding it from trace_smem here measured 1.3 % slower)
     int st;
     do {
         HitDraws dr;
-        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + id, t.hits, dr);
-        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + id, t.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, t, dr);
+        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, t.hits, dr);
+        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, t.hits, P.k.lobe_n, P.k.lobe_ang);
+        st = bounce_step<ROUGH, MODEL, false>(g, P.k, (float)g.zc, T, t, dr);
     } while (st == 0 && t.where != EV_WALL);
     return st;
 }
 
-struct QEntry { float4 a, b; };                     // pos.xyz, dir.x | dir.yz, idx, hits
+// The slow path of k_trace, out of line (one call per 32 port crossings): ptxas allocates the hot loop's registers without
+// seeing the double-precision code (inlined, the direction sink's acos / atan2 pushed the ray state of the bounce bodies
+// into local memory).  Entries q[0..take) are the crossings to resolve; resumed rays go to rq[nr..); returns the new nr.
+template <bool ROUGH, int MODEL, int SINK_>
+__device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const DrawTabs& T, altb_record* __restrict__ rec,
+                                                 const QEntry* q, QEntry* rq, uint32_t take, uint32_t nr) {
+    constexpr bool BATCHED = SINK_ == SINK_DIRECTION_BATCHED;
+    constexpr int SINK = SINK_ == SINK_RECORDS ? SINK_RECORDS : SINK_DIRECTION;
+    const uint32_t shift = BATCHED ? P.shift : 31u, imask = BATCHED ? P.imask : 0x7fffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    bool resume = false;
+    QEntry e;
+    if (lane < take) {
+        e = q[lane];
+        const uint32_t id = __float_as_uint(e.b.z);
+        const uint32_t slot = BATCHED ? id >> shift : 0u;
+        Geom g;
+        if (BATCHED) slot_geom(P, slot, g); else g = P.g;
+        const double xd[3] = {(double)e.a.x, (double)e.a.y, (double)e.a.z};
+        const double dd[3] = {(double)e.a.w, (double)e.b.x, (double)e.b.y};
+        double out[3];
+        const int kind = cap_crossing(g, xd, dd, out);
+        e.a.x = (float)out[0]; e.a.y = (float)out[1]; e.a.z = (float)out[2];
+        if (kind == EV_EXIT) {
+            if (SINK == SINK_RECORDS) {
+                float4* p = reinterpret_cast<float4*>(rec + id);
+                p[0] = e.a;
+                p[1] = make_float4(e.b.x, e.b.y, e.b.w, __uint_as_float((uint32_t)ALTB_EXITED));
+            } else exit_to_map(P, slot, e.a.z, e.a.w, e.b.x, e.b.y, __float_as_uint(e.b.w));
+        } else {
+            // Port-edge hit (4 % of the crossings, 3e-4 of the surface hits): bounce on the edge right here, with the
+            // generic step, until the ray is back on the inner sphere (resume) or ends.  Few lanes, rare.
+            RayState t;
+            t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
+            t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
+            const int st = edge_bounces<ROUGH, MODEL>(P, g, T, P.ctr_lo0 + (id & imask), t);
+            if (st == ALTB_EXITED && SINK == SINK_DIRECTION) exit_to_map(P, slot, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
+            else if (st) {
+                if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
+                else stat_end(trace_stats(P, P.n_slots, slot), st == ALTB_ABSORBED ? 2 : 3, t.hits);
+            } else {
+                resume = true;
+                e.a = make_float4(t.pos.x, t.pos.y, t.pos.z, t.dir.x);
+                e.b = make_float4(t.dir.y, t.dir.z, e.b.z, __uint_as_float(t.hits));
+            }
+        }
+    }
+    const unsigned rm = __ballot_sync(FULL, resume);
+    if (rm) {
+        if (nr + __popc(rm) > RQCAP) __trap();         // cannot happen (bounds above); never corrupt silently
+        if (resume) { QEntry* w = rq + nr + __popc(rm & ((1u << lane) - 1u)); __stcg(&w->a, e.a); __stcg(&w->b, e.b); }
+        nr += __popc(rm);
+    }
+    __syncwarp();
+    return nr;
+}
 
-static constexpr size_t TRACE_SMEM = TABS_BYTES + (size_t)TRACE_WARPS * (XQCAP + RQCAP) * sizeof(QEntry);
-
-template <bool ROUGH, int MODEL>
+template <bool ROUGH, int MODEL, int SINK_>
 __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constant__ TraceParams P,
                                                          altb_record* __restrict__ rec,
                                                          unsigned int* __restrict__ counter) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;
+    constexpr bool BATCHED = SINK_ == SINK_DIRECTION_BATCHED;      // single-slot instances read the port plane from the constant bank
+    constexpr int SINK = SINK_ == SINK_RECORDS ? SINK_RECORDS : SINK_DIRECTION;
+    const uint32_t shift = BATCHED ? P.shift : 31u, imask = BATCHED ? P.imask : 0x7fffffffu;
     QEntry* s_q = reinterpret_cast<QEntry*>(trace_smem + TABS_BYTES);
     for (int i = threadIdx.x; i < (int)(TABS_BYTES / sizeof(float4)); i += TRACE_THREADS)
         reinterpret_cast<float4*>(trace_smem)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
@@ -159,15 +270,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
     const DrawTabs T = make_tabs(trace_smem);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    QEntry* xq = s_q + (size_t)warp * (XQCAP + RQCAP);   // crossings waiting for the slow path
-    QEntry* rq = xq + XQCAP;                              // rays to resume (edge / wall events found by the slow path)
+    QEntry* xq = s_q + (size_t)warp * XQCAP;                                       // crossings waiting for the slow path
+    QEntry* rq = P.rq + ((size_t)blockIdx.x * TRACE_WARPS + warp) * RQCAP;         // rays to resume (global memory, rare)
     uint32_t nx = 0, nr = 0;          // warp-uniform queue fills
-    uint32_t next = 0, end = 0;       // warp-uniform: ids [next,end) are claimed by this warp
+    uint32_t next = 0, end = 0;       // warp-uniform: lane indices [next,end) (slot bits included) are claimed by this warp
     bool exhausted = false;           // warp-uniform: the global pool is empty
     bool alive = false;
     uint32_t idx = 0;
+    float zc = P.k.zc;                // BATCHED: port plane of this lane's ray
     RayState s;
     s.pos = {0.f, 0.f, 0.f}; s.dir = {0.f, 0.f, 0.f}; s.hits = 0; s.where = EV_WALL;
+
+    auto finish = [&](uint32_t id, const RayState& t, int st) {      // a ray that ended on the wall / edge (absorbed, suspended)
+        const uint32_t slot = BATCHED ? id >> shift : 0u;
+        if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
+        else stat_end(trace_stats(P, BATCHED ? P.n_slots : 1u, slot), st == ALTB_ABSORBED ? 2 : 3, t.hits);
+    };
 
     while (true) {
         // ---- regeneration
@@ -176,10 +294,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             if (nr) {                                   // resume parked rays first
                 const uint32_t rank = __popc(need & lt_mask);
                 if (!alive && rank < nr) {
-                    const QEntry e = rq[nr - 1 - rank];
-                    s.pos = {e.a.x, e.a.y, e.a.z}; s.dir = {e.a.w, e.b.x, e.b.y};
-                    idx = __float_as_uint(e.b.z);
-                    s.hits = __float_as_uint(e.b.w);
+                    const float4 ea = __ldcg(&rq[nr - 1 - rank].a), eb = __ldcg(&rq[nr - 1 - rank].b);
+                    s.pos = {ea.x, ea.y, ea.z}; s.dir = {ea.w, eb.x, eb.y};
+                    idx = __float_as_uint(eb.z);
+                    s.hits = __float_as_uint(eb.w);
+                    if (BATCHED) zc = P.slots[idx >> shift].zcf;
                     alive = true;
                 }
                 nr -= min(nr, (uint32_t)__popc(need));
@@ -188,16 +307,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             }
             if (need && !exhausted) {
                 if (next >= end) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(counter, P.chunk);
-                    base = __shfl_sync(FULL, base, 0);
-                    if (base >= P.n) { exhausted = true; next = end = 0; }
-                    else { next = base; end = min(base + P.chunk, P.n); }
+                    uint32_t q = 0;
+                    if (lane == 0) q = atomicAdd(counter, 1u);
+                    q = __shfl_sync(FULL, q, 0);
+                    if (q >= P.n_chunks) { exhausted = true; next = end = 0; }
+                    else {
+                        uint32_t slot = 0;
+                        if (BATCHED) { slot = q / P.cps; q -= slot * P.cps; }
+                        next = q * P.chunk; end = (slot << shift) + min(next + P.chunk, P.n);     // n < 2^shift: plain integers
+                        next += slot << shift;
+                    }
                 }
                 if (!alive) {
                     const uint32_t id = next + __popc(need & lt_mask);
                     if (id < end) {
                         alive = true; idx = id;
+                        if (BATCHED) zc = P.slots[id >> shift].zcf;
                         s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
                         s.hits = 0;
                     }
@@ -218,11 +343,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             bool crossing = false;
             if (alive) {
                 HitDraws dr;
-                hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + idx, s.hits, dr);
-                if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + idx, s.hits, P.k.lobe_n, P.k.lobe_ang);
-                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, T, s, dr);
+                const uint32_t ctr_lo = P.ctr_lo0 + (BATCHED ? idx & imask : idx);
+                hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, s.hits, dr);
+                if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, s.hits, P.k.lobe_n, P.k.lobe_ang);
+                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, BATCHED ? zc : P.k.zc, T, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
-                else if (st) { store_record(rec, idx, s, st); alive = false; }
+                else if (st) { finish(idx, s, st); alive = false; }
             }
             const unsigned cm = __ballot_sync(FULL, crossing);
             if (cm) {
@@ -239,46 +365,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         // ---- drain the crossing queue at full width (or whatever is left once nothing else can run)
         if (nx >= 32 || (nx && !any_alive && exhausted && nr == 0)) {
             const uint32_t take = min(nx, 32u);
-            const uint32_t base = nx - take;
-            bool resume = false;
-            QEntry e;
-            if (lane < take) {
-                e = xq[base + lane];
-                const double xd[3] = {(double)e.a.x, (double)e.a.y, (double)e.a.z};
-                const double dd[3] = {(double)e.a.w, (double)e.b.x, (double)e.b.y};
-                double out[3];
-                const int kind = cap_crossing(P.g, xd, dd, out);
-                e.a.x = (float)out[0]; e.a.y = (float)out[1]; e.a.z = (float)out[2];
-                if (kind == EV_EXIT) {
-                    float4* p = reinterpret_cast<float4*>(rec + __float_as_uint(e.b.z));
-                    p[0] = e.a;
-                    p[1] = make_float4(e.b.x, e.b.y, e.b.w, __uint_as_float((uint32_t)ALTB_EXITED));
-                } else {
-                    // Port-edge hit (4 % of the crossings, 3e-4 of the surface hits): bounce on the edge right here, with the
-                    // generic step, until the ray is back on the inner sphere (resume) or ends.  Few lanes, rare.
-                    const uint32_t id = __float_as_uint(e.b.z);
-                    RayState t;
-                    t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
-                    t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
-                    const int st = edge_bounces<ROUGH, MODEL>(P, T, id, t);
-                    if (st) store_record(rec, id, t, st);
-                    else {
-                        resume = true;
-                        e.a = make_float4(t.pos.x, t.pos.y, t.pos.z, t.dir.x);
-                        e.b = make_float4(t.dir.y, t.dir.z, e.b.z, __uint_as_float(t.hits));
-                    }
-                }
-            }
-            nx = base;
-            const unsigned rm = __ballot_sync(FULL, resume);
-            if (rm) {
-                if (nr + __popc(rm) > RQCAP) __trap();         // cannot happen (bounds above); never corrupt silently
-                if (resume) rq[nr + __popc(rm & lt_mask)] = e;
-                nr += __popc(rm);
-            }
-            __syncwarp();
+            nx -= take;
+            nr = drain_crossings<ROUGH, MODEL, SINK_>(P, T, rec, xq + nx, rq, take, nr);
         }
     }
+
+}
+
+// SINK_DIRECTION: the blocks' private statistics -> the scenes' 8 statistics words
+// (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces, 0, 0), added to.  One thread per (slot, word).
+__global__ void k_reduce_trace_stats(const __grid_constant__ TraceParams P, int n_blocks) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_slots * STAT_WORDS) return;
+    const uint32_t slot = t / STAT_WORDS, w = t % STAT_WORDS;
+    unsigned long long v = 0;
+    for (int b = 0; b < n_blocks; b++) v += P.gstat[((size_t)b * P.n_slots + slot) * STAT_WORDS + w];
+    if (!v) return;
+    unsigned long long* g = P.stats_base + (size_t)P.slots[slot].scene * 8;
+    // words: 0 exited, 1 port, 2 absorbed, 3 suspended, 4 bounces
+    const int dst[STAT_WORDS] = {1, 2, 3, 4, 5};
+    atomicAdd(g + dst[w], v);
+    if (w == 0 || w == 2 || w == 3) atomicAdd(g + 0, v);      // every finished ray is exactly one of exited / absorbed / suspended
 }
 
 // Generic one-thread-per-ray tracer with the in-line step: used when the source's first event is the port edge itself
@@ -295,11 +402,25 @@ __global__ void __launch_bounds__(128) k_trace_generic(const __grid_constant__ T
     int st = 0;
     while (!st) {
         HitDraws dr;
-        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, P.ray_id0 + i, s.hits, dr);
-        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, P.ray_id0 + i, s.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, s, dr);
+        const uint64_t rid = P.ray_id0 + i;
+        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), s.hits, dr);
+        if (MODEL == 3) dr.u_r = lobe_accept(P.keys, rid, s.hits, P.k.lobe_n, P.k.lobe_ang);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, T, s, dr);
     }
     store_record(rec, i, s, st);
+}
+
+// every source ray leaves through the port without touching anything, DIRECTION map: n identical rays, one bin
+__global__ void k_all_exit_direction(altb_record proto, unsigned long long n, int n_theta, int n_phi, float exit_zf,
+                                     unsigned long long* __restrict__ counts, unsigned long long* __restrict__ stats) {
+    if (blockIdx.x || threadIdx.x) return;
+    atomicAdd(stats + 0, n); atomicAdd(stats + 1, n);
+    if (proto.pos[2] < exit_zf) {
+        atomicAdd(stats + 2, n);
+        const f3 d = {proto.dir[0], proto.dir[1], proto.dir[2]};
+        const int b = direction_bin(n_theta, n_phi, d);
+        if (b >= 0) atomicAdd(counts + b, n);
+    }
 }
 
 // every source ray leaves through the port without touching anything
@@ -347,7 +468,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
         HitDraws h;
         hit_from_draws(dr, P.k.rho, P.k.p_spec, h);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, T, s, h);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, T, s, h);
     }
     store_record(rec, i, s, st);
 }

@@ -286,12 +286,11 @@ def _run_ours(args):
     map_crc = "%08x" % (zlib.crc32(np.ascontiguousarray(c_probe).tobytes() + np.ascontiguousarray(s_probe[:, :6]).tobytes()) & 0xffffffff)
 
     # ---- per-kernel timing for the roofline (CUDA events inside the library, on its own stream, around the trace launches)
-    l0 = ctx.launches
+    l0, tl0 = ctx.launches, ctx.trace_launches
     _, kst = ctx.trace_fluxmap(sc, src, total // world, mp, seed=4357, ray_id0=next_id[0] + rank * (total // world))
-    k_launches = ctx.launches - l0
+    k_launches, n_trace = ctx.launches - l0, max(1, ctx.trace_launches - tl0)
     kst = kst[0]
     peak = ctx.measure_fp32_peak()
-    n_trace = max(1, ctx.trace_launches_last) if hasattr(ctx, "trace_launches_last") else max(1, -(-(total // world) // (1 << 28)))
     achieved = FLOP_PER_BOUNCE * kst["n_bounces"] / kst["t_trace_s"] * 1e-12
     roofline = {"bound": "fp32", "kernel": "k_trace<rough,CustomMirror>", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,

@@ -88,12 +88,16 @@ void altb_destroy(altb_ctx* ctx);
 const char* altb_last_error(void);
 int  altb_version(void);
 int  altb_device_count(void);
-/* batch = rays per trace launch (default 2^28); 0 keeps the default. */
+/* batch = rays per trace launch; 0 restores the defaults: 2^28 where the trace writes 32-byte records (LINE-type maps,
+ * per-ray results), 2^32 / n_scenes where it bins in the kernel (DIRECTION maps: nothing is stored per ray). */
 int  altb_set_batch(altb_ctx* ctx, uint64_t batch_rays);
 
 /* THE HOT PATH.  For each scene: trace rays ray_id0 .. ray_id0+n_rays-1 (ray i's random stream
  * depends only on (seed, i)) and accumulate the flux map.  counts[n_scenes][n_theta*n_phi] is
- * theta-major like the CSV rows and is ADDED to.  Replaces TraceNonSequential(ARayArray*) + the
+ * theta-major like the CSV rows and is ADDED to.  BATCHED SCENES: in DIRECTION mode, scenes that differ only in
+ * theta_max_deg (a port-angle series, fluxAtObserverFast.C:1641-1673) share ONE persistent launch per device (up to 192
+ * scenes per launch; the scene index is part of the claimed work unit), instead of one launch and one kernel tail per
+ * scene; any other mix of scenes is traced group by group.  Replaces TraceNonSequential(ARayArray*) + the
  * GetExited()/checkIntersection loops: fluxAtObserverOptimize.C:281-333, fluxAtObserverFast.C:1144-1303. */
 int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n_scenes, const altb_source* src,
                        uint64_t ray_id0, uint64_t n_rays, uint64_t seed, const altb_map_spec* map,
@@ -156,6 +160,8 @@ int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t altb_launch_count(const altb_ctx* ctx);
+/* ... of which launches of the bounce-loop kernel k_trace (bench.py: average launch duration of the roofline). */
+uint64_t altb_trace_launch_count(const altb_ctx* ctx);
 
 #ifdef __cplusplus
 }

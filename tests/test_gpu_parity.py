@@ -191,6 +191,93 @@ def test_multi_scene_and_empty(ctx, oracle, altb):
     assert z_counts.sum() == 0 and z_st[0]["n_rays"] == 0
 
 
+def _direction_oracle(oracle, kw, n, seed=SEED, ray_id0=0, src=None):
+    return oracle.fluxmap(oracle.scene(**kw), src or oracle.source(), n, oracle.map_spec(mode=oracle.MAP_DIRECTION), seed=seed,
+                          ray_id0=ray_id0, prec=oracle.F32)
+
+
+def test_batched_scenes_one_launch(ctx, oracle, altb):
+    """Port-angle series (fluxAtObserverFast.C:1641-1673): scenes that differ only in theta_max share ONE persistent launch,
+    the scene index is part of the claimed work unit; maps and statistics must equal the oracle's scene by scene."""
+    thetas = [100.0, 137.5, 139.0, 150.0, 160.0, 163.0, 164.0, 166.0, 169.0, 170.0, 172.0, 175.0, 178.0, 179.5]
+    n = 30_011
+    gm = altb.map_spec(mode=altb.MAP_DIRECTION)
+    l0, t0 = ctx.launches, ctx.trace_launches
+    g_counts, g_st = ctx.trace_fluxmap([altb.scene(theta_max=t) for t in thetas], altb.source(), n, gm, seed=SEED, ray_id0=77)
+    walls = sum(1 for t in thetas if t >= 139.0)                 # below 138.5 deg the pencil beam leaves through the port at once
+    assert ctx.trace_launches - t0 == 1, "the scenes whose first event is the wall must share one k_trace launch"
+    for i, t in enumerate(thetas):
+        o_counts, o_st = _direction_oracle(oracle, dict(theta_max=t), n, ray_id0=77)
+        assert np.array_equal(g_counts[i], o_counts), t
+        for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+            assert g_st[i][key] == o_st[key], (t, key)
+    assert walls == 12 and g_st[0]["n_bounces"] == 0 and g_st[0]["n_exit_port"] == n
+    # the same through per-scene launches (ALTB_NO_BATCH is read per call)
+    import os
+    os.environ["ALTB_NO_BATCH"] = "1"
+    try:
+        t0 = ctx.trace_launches
+        s_counts, s_st = ctx.trace_fluxmap([altb.scene(theta_max=t) for t in thetas], altb.source(), n, gm, seed=SEED, ray_id0=77)
+        assert ctx.trace_launches - t0 == walls
+    finally:
+        del os.environ["ALTB_NO_BATCH"]
+    assert np.array_equal(s_counts, g_counts) and [a["n_bounces"] for a in s_st] == [a["n_bounces"] for a in g_st]
+
+
+def test_batched_scenes_160_and_mixed_groups(ctx, oracle, altb):
+    """BASELINE config C5 shape: 160 port angles in one call; plus a call that mixes scenes which cannot share a launch
+    (different reflectance / BRDF / count_all) with ones that can -- each group goes its own way, results per scene."""
+    thetas = [100.0 + 0.5 * k for k in range(160)]
+    n = 4_003
+    gm = altb.map_spec(mode=altb.MAP_DIRECTION)
+    t0 = ctx.trace_launches
+    g_counts, g_st = ctx.trace_fluxmap([altb.scene(theta_max=t) for t in thetas], altb.source(), n, gm, seed=11)
+    assert ctx.trace_launches - t0 == 1
+    for i in (0, 76, 77, 78, 100, 140, 159):
+        o_counts, o_st = _direction_oracle(oracle, dict(theta_max=thetas[i]), n, seed=11)
+        assert np.array_equal(g_counts[i], o_counts), thetas[i]
+        assert g_st[i]["n_bounces"] == o_st["n_bounces"] and g_st[i]["n_absorbed"] == o_st["n_absorbed"]
+    tot = sum(s["n_exited"] + s["n_absorbed"] + s["n_suspended"] for s in g_st)
+    assert tot == 160 * n and all(s["n_rays"] == n for s in g_st)
+    kws = [dict(theta_max=165.0), dict(theta_max=170.0, reflectance=0.95), dict(theta_max=172.0),
+           dict(theta_max=170.0, brdf_kind=1), dict(theta_max=178.0, count_all_status=1), dict(theta_max=168.0, brdf_kind=1),
+           dict(theta_max=171.0, roughness=0.0), dict(theta_max=150.0)]
+    n = 20_000
+    t0 = ctx.trace_launches
+    g_counts, g_st = ctx.trace_fluxmap([altb.scene(**kw) for kw in kws], altb.source(), n, gm, seed=SEED)
+    assert ctx.trace_launches - t0 == 5          # {165,172,150}, {0.95}, {CustomMirror 170,168}, {count_all: record path}, {sigma 0}
+    for i, kw in enumerate(kws):
+        o_counts, o_st = _direction_oracle(oracle, kw, n)
+        assert np.array_equal(g_counts[i], o_counts), kw
+        for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+            assert g_st[i][key] == o_st[key], (kw, key)
+
+
+def test_direction_sink_batches_and_id_windows(ctx, oracle, altb):
+    """In-kernel binning with ragged launch sizes, and ray ids that straddle a multiple of 2^32 (the launch is split there:
+    the high counter word is uniform inside a launch)."""
+    gm = altb.map_spec(mode=altb.MAP_DIRECTION)
+    kw = dict(theta_max=170.0, brdf_kind=1)
+    n = 50_021
+    ctx.set_batch(7_001)
+    try:
+        a_counts, a_st = ctx.trace_fluxmap([altb.scene(**kw), altb.scene(**dict(kw, theta_max=160.0))], altb.source(), n, gm, seed=5)
+    finally:
+        ctx.set_batch(0)
+    for i, t in enumerate((170.0, 160.0)):
+        o_counts, o_st = _direction_oracle(oracle, dict(kw, theta_max=t), n, seed=5)
+        assert np.array_equal(a_counts[i], o_counts) and a_st[i]["n_bounces"] == o_st["n_bounces"]
+    id0 = (1 << 32) - 20_000
+    t0 = ctx.trace_launches
+    g_counts, g_st = ctx.trace_fluxmap(altb.scene(**kw), altb.source(), n, gm, seed=5, ray_id0=id0)
+    assert ctx.trace_launches - t0 == 2
+    o_counts, o_st = _direction_oracle(oracle, kw, n, seed=5, ray_id0=id0)
+    assert np.array_equal(g_counts[0], o_counts) and g_st[0]["n_bounces"] == o_st["n_bounces"]
+    g_rec, _ = ctx.trace_records(altb.scene(**kw), altb.source(), n, seed=5, ray_id0=id0)
+    o_rec, _ = oracle.trace(oracle.scene(**kw), oracle.source(), n, seed=5, ray_id0=id0, prec=oracle.F32)
+    assert _records_equal(g_rec, o_rec)
+
+
 def test_source_through_port_and_errors(ctx, oracle, altb):
     # a source aimed straight at the port: every ray leaves untouched
     src_g, src_o = altb.source((0, 0, -50), (0, 0, -1)), oracle.source((0, 0, -50), (0, 0, -1))

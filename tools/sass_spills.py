@@ -26,17 +26,21 @@ for name, ins in funcs.items():
     ph = [a for a, t in ins if "IMAD.WIDE.U32" in t]
     clusters = []
     for a in ph:
-        if not clusters or a - clusters[-1][1] > 0x400:
-            clusters.append([a, a])
+        if not clusters or a - clusters[-1][1] > 0x60:
+            clusters.append([a, a, 0])
         clusters[-1][1] = a
-    big = [c for c in clusters if c[1] - c[0] >= 0x100]          # full 10-round blocks
-    hot = (big[0][0], big[1][1] + 0x1800) if len(big) >= 2 else (0, 0)
-    # the second body ends where the drain's FP64 work starts
-    f64 = [a for a, t in ins if re.match(r"D(ADD|MUL|FMA|SETP)", t) and a > (big[1][1] if len(big) >= 2 else 0)]
-    if f64 and len(big) >= 2:
-        hot = (big[0][0], f64[0])
+        clusters[-1][2] += 1
+    big = [c for c in clusters if c[2] >= 20]                    # full 10-round blocks (20 wide multiplies)
+    # bounce bodies: from the first Philox block of the hot loop to one body length past the last one
+    hot = (0, 0)
+    if len(big) >= 2:
+        body = big[1][0] - big[0][0]
+        n_unrolled = 1
+        while n_unrolled < len(big) and abs((big[n_unrolled][0] - big[n_unrolled - 1][0]) - body) < 0x300:
+            n_unrolled += 1
+        hot = (big[0][0], big[n_unrolled - 1][0] + body)
     loc = [(a, t) for a, t in ins if re.search(r"\b(STL|LDL)", t)]
     inside = [a for a, t in loc if hot[0] <= a <= hot[1]]
-    tag = re.search(r"k_traceILb(\d)ELi(\d)", name)
-    print(f"k_trace<{tag.group(1)},{tag.group(2)}>: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
+    tag = re.search(r"k_traceILb(\d)ELi(\d)ELi(\d)", name)
+    print(f"k_trace<{tag.group(1)},{tag.group(2)},{tag.group(3)}>: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
           f"local-memory instructions: {len(inside)} in the bounce bodies, {len(loc) - len(inside)} elsewhere")
