@@ -46,6 +46,7 @@ struct DevCtx {
     // LINE-map tables of the last map spec (setup_map)
     bool map_cached = false; altb_map_spec map_key; MapParams map_M; int map_n_tiles = 0; size_t map_line_smem = 0;
     std::vector<float> tab_host; std::vector<float4> tiles_host;
+    double* dirtab = nullptr; uint64_t dirtab_cap = 0; int dir_nt = 0, dir_np = 0; std::vector<double> dirtab_host;    // direction_bin edges
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -132,7 +133,7 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.sincos);
-        cudaFree(d.rec2); cudaFree(d.counter2); cudaFree(d.rq[0]); cudaFree(d.rq[1]); cudaFree(d.gstat[0]); cudaFree(d.gstat[1]); cudaFree(d.stats_scratch);
+        cudaFree(d.rec2); cudaFree(d.counter2); cudaFree(d.rq[0]); cudaFree(d.rq[1]); cudaFree(d.gstat[0]); cudaFree(d.gstat[1]); cudaFree(d.stats_scratch); cudaFree(d.dirtab);
         for (auto& a : d.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
         if (d.fork_ev) cudaEventDestroy(d.fork_ev);
         for (auto& e : d.join_ev) if (e) cudaEventDestroy(e);
@@ -284,7 +285,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         for (int i = 0; i < 3; i++) { proto.pos[i] = (float)P.x0[i]; proto.dir[i] = (float)P.d0[i]; }
         proto.n_hits = 0; proto.status = ALTB_EXITED;
         if (sink == SINK_DIRECTION)
-            k_all_exit_direction<<<1, 32, 0, st>>>(proto, n, P.n_theta, P.n_phi, P.k.exit_zf, P.counts_base + (size_t)P.slots[0].scene * P.nb,
+            k_all_exit_direction<<<1, 32, 0, st>>>(proto, n, P.n_theta, P.n_phi, P.dir_tab, P.k.exit_zf, P.counts_base + (size_t)P.slots[0].scene * P.nb,
                                                    P.stats_base + (size_t)P.slots[0].scene * 8);
         else k_fill_records<<<d.sm_count * 4, 256, 0, st>>>(rec, n, proto);
         ctx->launches++;
@@ -331,7 +332,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     ctx->trace_launches++;
     CK(le);
     if (sink == SINK_DIRECTION) {
-        k_reduce_trace_stats<<<(P.n_slots * STAT_WORDS + 127) / 128, 128, 0, st>>>(P, blocks);
+        k_reduce_trace_stats<<<(P.n_slots + 63) / 64, 64, 0, st>>>(P, blocks);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -367,7 +368,24 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     M.use_smem_hist = ms.dir_smem <= 160 * 1024;
     if (!M.use_smem_hist) ms.dir_smem = 0;
     ms.n_tiles = 0; ms.line_smem = 0;
-    if (map->map_mode == ALTB_MAP_DIRECTION) return 0;
+    if (map->map_mode == ALTB_MAP_DIRECTION) {
+        // bin edges of direction_bin: cos(i w_theta), i = 0..n_theta; (cos, sin)(j w_phi), j = 0..n_phi (the last one = the first)
+        if (d.dir_nt != nt || d.dir_np != np) {
+            if (d.dir_nt) CK(cudaDeviceSynchronize());                    // kernels of an earlier call may still read the old table
+            std::vector<double>& t = d.dirtab_host;
+            t.assign((size_t)nt + 1 + 2 * ((size_t)np + 1), 0.0);
+            for (int i = 0; i <= nt; i++) t[i] = i == 0 ? 1.0 : cos(i * (90.0 / nt) * PI_D / 180.0);
+            for (int j = 0; j <= np; j++) {
+                const double a = (j % np) * (360.0 / np) * PI_D / 180.0;
+                t[(size_t)nt + 1 + j] = cos(a); t[(size_t)nt + 1 + np + 1 + j] = sin(a);
+            }
+            if (int rc = ensure(d.dirtab, d.dirtab_cap, (uint64_t)t.size())) return rc;
+            CK(cudaMemcpyAsync(d.dirtab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            d.dir_nt = nt; d.dir_np = np;
+        }
+        M.dir_tab = d.dirtab;
+        return 0;
+    }
     (void)grouped;
     if (!(map->det_radius > 0) || !(map->det_width > 0)) return fail(ALTB_E_ARG, "map: det_radius/det_width must be > 0");
 
@@ -599,7 +617,7 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
             ts.P.n_slots = (uint32_t)g.size();
             for (size_t j = 0; j < g.size(); j++) { ts.P.slots[j] = tss[g[j]].P.slots[0]; ts.P.slots[j].scene = (uint32_t)g[j]; }
             ts.P.counts_base = d_counts; ts.P.stats_base = d_stats;
-            ts.P.nb = (uint32_t)nb; ts.P.n_theta = map->n_theta; ts.P.n_phi = map->n_phi;
+            ts.P.nb = (uint32_t)nb; ts.P.n_theta = map->n_theta; ts.P.n_phi = map->n_phi; ts.P.dir_tab = ms.M.dir_tab;
         }
         const uint64_t cap = dsink ? dir_cap(g.size()) : batch_rec;
         MapSetup msg = ms;

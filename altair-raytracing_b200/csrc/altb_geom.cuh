@@ -59,6 +59,7 @@ struct TraceParams {
     // SINK_DIRECTION: the maps / statistics the kernel adds to, bins of the direction map
     unsigned long long* counts_base; unsigned long long* stats_base;
     uint32_t nb; int n_theta, n_phi;
+    const double* dir_tab;   // bin edges of the direction map (altb_kernels.cuh: direction_bin)
     const float2* sincos; // device tables: SC_N sin/cos entries + LG_N log entries (altb_math.cuh: DrawTabs)
     SceneSlot slots[MAX_SLOTS];
 };

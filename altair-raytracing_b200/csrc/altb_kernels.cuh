@@ -167,7 +167,7 @@ __device__ __forceinline__ void slot_geom(const TraceParams& P, uint32_t slot, G
     g.zc = sl->zc; g.T2 = sl->T2; g.cth = sl->cth; g.sth = sl->sth;
 }
 
-__device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const f3& d);
+__device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const double* __restrict__ tab, const f3& d);
 
 // SINK_DIRECTION: an exited ray (world-box point pos, direction dir).  Out of line: double-precision acos / atan2 must not
 // cost the hot loop any registers.
@@ -177,7 +177,7 @@ __device__ __noinline__ void exit_to_map(const TraceParams& P, uint32_t slot, fl
     if (pos_z < P.k.exit_zf) {
         atomicAdd(gs + 1, 1ull);
         const f3 d = {dx, dy, dz};
-        const int b = direction_bin(P.n_theta, P.n_phi, d);
+        const int b = direction_bin(P.n_theta, P.n_phi, P.dir_tab, d);
         if (b >= 0) atomicAdd(P.counts_base + (size_t)P.slots[slot].scene * P.nb + b, 1ull);
     }
 }
@@ -237,7 +237,8 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
             if (st == ALTB_EXITED && SINK == SINK_DIRECTION) exit_to_map(P, slot, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
             else if (st) {
                 if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
-                else stat_end(trace_stats(P, P.n_slots, slot), st == ALTB_ABSORBED ? 2 : 3, t.hits);
+                else if (st == ALTB_ABSORBED) atomicAdd(trace_stats(P, P.n_slots, slot) + 4, (unsigned long long)t.hits);
+                else stat_end(trace_stats(P, P.n_slots, slot), 3, t.hits);
             } else {
                 resume = true;
                 e.a = make_float4(t.pos.x, t.pos.y, t.pos.z, t.dir.x);
@@ -284,7 +285,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
     auto finish = [&](uint32_t id, const RayState& t, int st) {      // a ray that ended on the wall / edge (absorbed, suspended)
         const uint32_t slot = BATCHED ? id >> shift : 0u;
         if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
-        else stat_end(trace_stats(P, BATCHED ? P.n_slots : 1u, slot), st == ALTB_ABSORBED ? 2 : 3, t.hits);
+        else {       // absorbed rays are not counted one by one: absorbed = rays - exited - suspended (k_reduce_trace_stats)
+            unsigned long long* gs = trace_stats(P, BATCHED ? P.n_slots : 1u, slot);
+            if (st == ALTB_ABSORBED) atomicAdd(gs + 4, (unsigned long long)t.hits);
+            else stat_end(gs, 3, t.hits);
+        }
     };
 
     while (true) {
@@ -373,19 +378,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
 }
 
 // SINK_DIRECTION: the blocks' private statistics -> the scenes' 8 statistics words
-// (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces, 0, 0), added to.  One thread per (slot, word).
+// (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces, 0, 0), added to.  One thread per slot.
 __global__ void k_reduce_trace_stats(const __grid_constant__ TraceParams P, int n_blocks) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n_slots * STAT_WORDS) return;
-    const uint32_t slot = t / STAT_WORDS, w = t % STAT_WORDS;
-    unsigned long long v = 0;
-    for (int b = 0; b < n_blocks; b++) v += P.gstat[((size_t)b * P.n_slots + slot) * STAT_WORDS + w];
-    if (!v) return;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.n_slots) return;
+    unsigned long long v[STAT_WORDS] = {0, 0, 0, 0, 0};      // exited, port, (unused), suspended, bounces
+    for (int b = 0; b < n_blocks; b++)
+        for (int w = 0; w < STAT_WORDS; w++) v[w] += P.gstat[((size_t)b * P.n_slots + slot) * STAT_WORDS + w];
     unsigned long long* g = P.stats_base + (size_t)P.slots[slot].scene * 8;
-    // words: 0 exited, 1 port, 2 absorbed, 3 suspended, 4 bounces
-    const int dst[STAT_WORDS] = {1, 2, 3, 4, 5};
-    atomicAdd(g + dst[w], v);
-    if (w == 0 || w == 2 || w == 3) atomicAdd(g + 0, v);      // every finished ray is exactly one of exited / absorbed / suspended
+    // every ray of the launch ended as exactly one of exited / absorbed / suspended; the absorbed ones are not counted one by one
+    atomicAdd(g + 0, (unsigned long long)P.n);
+    atomicAdd(g + 1, v[0]); atomicAdd(g + 2, v[1]);
+    atomicAdd(g + 3, (unsigned long long)P.n - v[0] - v[3]);
+    atomicAdd(g + 4, v[3]); atomicAdd(g + 5, v[4]);
 }
 
 // Generic one-thread-per-ray tracer with the in-line step: used when the source's first event is the port edge itself
@@ -411,14 +416,14 @@ __global__ void __launch_bounds__(128) k_trace_generic(const __grid_constant__ T
 }
 
 // every source ray leaves through the port without touching anything, DIRECTION map: n identical rays, one bin
-__global__ void k_all_exit_direction(altb_record proto, unsigned long long n, int n_theta, int n_phi, float exit_zf,
-                                     unsigned long long* __restrict__ counts, unsigned long long* __restrict__ stats) {
+__global__ void k_all_exit_direction(altb_record proto, unsigned long long n, int n_theta, int n_phi, const double* __restrict__ dir_tab,
+                                     float exit_zf, unsigned long long* __restrict__ counts, unsigned long long* __restrict__ stats) {
     if (blockIdx.x || threadIdx.x) return;
     atomicAdd(stats + 0, n); atomicAdd(stats + 1, n);
     if (proto.pos[2] < exit_zf) {
         atomicAdd(stats + 2, n);
         const f3 d = {proto.dir[0], proto.dir[1], proto.dir[2]};
-        const int b = direction_bin(n_theta, n_phi, d);
+        const int b = direction_bin(n_theta, n_phi, dir_tab, d);
         if (b >= 0) atomicAdd(counts + b, n);
     }
 }
@@ -486,6 +491,7 @@ struct MapParams {
     const float4* supers;          // [n_super]: same for blocks of SUPER x SUPER tiles
     int t_theta, t_phi, nt_theta, nt_phi;                                // tile shape / tile grid
     int use_smem_hist;
+    const double* dir_tab;         // DIRECTION mode: bin edges (direction_bin)
     int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
 };
 
@@ -537,17 +543,30 @@ __global__ void __launch_bounds__(256) k_stats(const altb_record* __restrict__ r
 }
 
 // ------------------------------------------------------------------------------------ K2a direction map
-__device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const f3& d) {
+// Bin of an exit direction: theta = acos(-d.z) in [0, 90) deg, phi = atan2(d.y, d.x) in [0, 360) deg, bin = floor(angle / width)
+// (the TH2D axes of fluxAtObserverFast.C:1092-1093).  Evaluated without double-precision acos / atan2: a single-precision
+// estimate of the bin, then ONE exact correction step against the bin edges in double --
+//   theta bin i  <=>  cos((i+1) w) <  c <= cos(i w)                      (tab[0 .. n_theta]        = cos(i w_theta))
+//   phi bin j    <=>  e_j x d >= 0  and  e_(j+1) x d < 0                 (tab[n_theta+1 ..]        = cos(j w_phi), sin(j w_phi))
+// which is the same bin as the floor of the double-precision angle unless the direction lies within one double rounding
+// error of an edge (the same caveat as comparing two libm implementations).  ~60 instead of ~450 instructions per ray.
+__device__ __forceinline__ int direction_bin(int n_theta, int n_phi, const double* __restrict__ tab, const f3& d) {
     if (!(d.z < 0.0f)) return -1;
-    double c = -(double)d.z;
-    if (c > 1.0) c = 1.0;
-    const double th = acos(c) * (180.0 / 3.14159265358979323846);
-    double ph = atan2((double)d.y, (double)d.x) * (180.0 / 3.14159265358979323846);
-    if (ph < 0.0) ph += 360.0;
-    int i = (int)floor(th / (90.0 / n_theta));
-    int j = (int)floor(ph / (360.0 / n_phi));
+    const float cf = fminf(-d.z, 1.0f);
+    const double c = (double)cf;
+    int i = (int)(acosf(cf) * ((float)n_theta * 0.63661977f));
     i = min(max(i, 0), n_theta - 1);
+    if (c > __ldg(tab + i)) i = max(i - 1, 0);
+    else if (!(c > __ldg(tab + i + 1))) i = min(i + 1, n_theta - 1);
+    const double* ex = tab + n_theta + 1;
+    const double* ey = ex + n_phi + 1;
+    float ph = atan2f(d.y, d.x);
+    if (ph < 0.0f) ph += 6.2831855f;
+    int j = (int)(ph * ((float)n_phi * 0.15915494f));
     j = min(max(j, 0), n_phi - 1);
+    const double dx = (double)d.x, dy = (double)d.y;
+    if (__ldg(ex + j) * dy - __ldg(ey + j) * dx < 0.0) j = j == 0 ? n_phi - 1 : j - 1;
+    else if (!(__ldg(ex + j + 1) * dy - __ldg(ey + j + 1) * dx < 0.0)) j = j + 1 == n_phi ? 0 : j + 1;
     return i * n_phi + j;
 }
 
@@ -573,7 +592,7 @@ __global__ void __launch_bounds__(DIR_THREADS) k_map_direction(const altb_record
         if (lane < cnt) {
             const float4 e = q[first + lane];
             const f3 dir = {e.x, e.y, e.z};
-            const int b = direction_bin(M.n_theta, M.n_phi, dir);
+            const int b = direction_bin(M.n_theta, M.n_phi, M.dir_tab, dir);
             if (b >= 0 && counts) {
                 if (M.use_smem_hist) atomicAdd(&hist[b], 1u);
                 else atomicAdd(counts + b, 1ull);

@@ -211,7 +211,8 @@ def test_batched_scenes_one_launch(ctx, oracle, altb):
         assert np.array_equal(g_counts[i], o_counts), t
         for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
             assert g_st[i][key] == o_st[key], (t, key)
-    assert walls == 12 and g_st[0]["n_bounces"] == 0 and g_st[0]["n_exit_port"] == n
+    # theta_max = 100: the beam leaves untouched, through the SIDE of the world box (z = -75 > exit_z): exited, not "port"
+    assert walls == 12 and g_st[0]["n_bounces"] == 0 and g_st[0]["n_exited"] == n and g_st[0]["n_exit_port"] == 0
     # the same through per-scene launches (ALTB_NO_BATCH is read per call)
     import os
     os.environ["ALTB_NO_BATCH"] = "1"
