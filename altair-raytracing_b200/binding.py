@@ -14,6 +14,7 @@ _LIB_PATH = os.environ.get("ALTB_LIB") or os.path.join(_PKG, "libaltair_b200.so"
 
 EXITED, ABSORBED, SUSPENDED, TAPE_END = 1, 2, 3, 4
 MAP_LINE, MAP_TRACEONCE_COMPAT, MAP_DIRECTION, MAP_PER_POSITION, MAP_TWOFOLD = 0, 1, 2, 3, 4
+CONTRACT_EXACT, CONTRACT_FAST = 0, 1
 
 RECORD_DTYPE = np.dtype([("pos", "<f4", 3), ("dir", "<f4", 3), ("n_hits", "<u4"), ("status", "<u4")])
 
@@ -111,6 +112,8 @@ def load_library():
     L.altb_destroy.argtypes = [vp]
     L.altb_destroy.restype = None
     L.altb_set_batch.argtypes = [vp, u64]
+    L.altb_set_contract.argtypes = [vp, C.c_int]
+    L.altb_get_contract.argtypes = [vp]
     L.altb_launch_count.argtypes = [vp]
     L.altb_launch_count.restype = u64
     L.altb_trace_launch_count.argtypes = [vp]
@@ -177,6 +180,14 @@ class Context:
     @property
     def trace_launches(self):
         return int(self._L.altb_trace_launch_count(self._h))
+
+    def set_contract(self, contract):
+        """CONTRACT_EXACT (bit-exact vs the CPU oracle, default) or CONTRACT_FAST (special-function unit; include/altair_b200.h)."""
+        self._check(self._L.altb_set_contract(self._h, int(contract)))
+
+    @property
+    def contract(self):
+        return int(self._L.altb_get_contract(self._h))
 
     def set_batch(self, batch_rays):
         self._check(self._L.altb_set_batch(self._h, int(batch_rays)))

@@ -55,6 +55,7 @@ struct DevCtx {
 struct altb_ctx {
     std::vector<DevCtx> devs;
     uint64_t batch = DEFAULT_BATCH;
+    int contract = ALTB_CONTRACT_EXACT;
     bool batch_user = false;          // altb_set_batch was called: the direction sink honours it too (default there: 2^31)
     uint64_t launches = 0;
     uint64_t trace_launches = 0;      // k_trace launches only (roofline: average launch duration)
@@ -207,6 +208,14 @@ extern "C" int altb_set_batch(altb_ctx* ctx, uint64_t batch_rays) {
     return 0;
 }
 
+extern "C" int altb_set_contract(altb_ctx* ctx, int contract) {
+    if (!ctx) return fail(ALTB_E_ARG, "ctx is NULL");
+    if (contract != ALTB_CONTRACT_EXACT && contract != ALTB_CONTRACT_FAST) return fail(ALTB_E_ARG, "altb_set_contract: unknown contract %d", contract);
+    ctx->contract = contract;
+    return 0;
+}
+extern "C" int altb_get_contract(const altb_ctx* ctx) { return ctx ? ctx->contract : -1; }
+
 extern "C" uint64_t altb_launch_count(const altb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t altb_trace_launch_count(const altb_ctx* ctx) { return ctx ? ctx->trace_launches : 0; }
 
@@ -253,18 +262,46 @@ static bool same_launch(const TraceSetup& a, const TraceSetup& b) {
            memcmp(&a.P.keys, &b.P.keys, sizeof a.P.keys) == 0;
 }
 
-template <bool R, int M, int S>
+template <bool R, int M, int S, int C>
 static cudaError_t launch_trace_t(const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
     static thread_local int attr_dev = -1;      // the opt-in to >48 kB of dynamic shared memory is per device and per kernel
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_trace<R, M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_trace<R, M, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
         if (e != cudaSuccess) return e;
         attr_dev = dev;
     }
-    k_trace<R, M, S><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
+    k_trace<R, M, S, C><<<blocks, TRACE_THREADS, TRACE_SMEM, st>>>(P, rec, counter);
     return cudaGetLastError();
+}
+
+// kernel instance = (roughness on/off, reflection model, sink, arithmetic contract); the fast contract is built for the
+// Lambert and CustomMirror models (0, 1)
+template <int S, int C>
+static cudaError_t launch_trace_sc(bool rough, int model, const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
+    if (rough) {
+        if (model == 0) return launch_trace_t<true, 0, S, C>(P, rec, counter, blocks, st);
+        if (model == 1) return launch_trace_t<true, 1, S, C>(P, rec, counter, blocks, st);
+        if constexpr (C == CONTRACT_EXACT) {
+            if (model == 2) return launch_trace_t<true, 2, S, C>(P, rec, counter, blocks, st);
+            return launch_trace_t<true, 3, S, C>(P, rec, counter, blocks, st);
+        }
+    } else {
+        if (model == 0) return launch_trace_t<false, 0, S, C>(P, rec, counter, blocks, st);
+        if (model == 1) return launch_trace_t<false, 1, S, C>(P, rec, counter, blocks, st);
+        if constexpr (C == CONTRACT_EXACT) {
+            if (model == 2) return launch_trace_t<false, 2, S, C>(P, rec, counter, blocks, st);
+            return launch_trace_t<false, 3, S, C>(P, rec, counter, blocks, st);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+template <int C>
+static cudaError_t launch_trace_c(int sink, bool rough, int model, const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
+    if (sink != SINK_DIRECTION) return launch_trace_sc<SINK_RECORDS, C>(rough, model, P, rec, counter, blocks, st);
+    if (P.n_slots > 1) return launch_trace_sc<SINK_DIRECTION_BATCHED, C>(rough, model, P, rec, counter, blocks, st);
+    return launch_trace_sc<SINK_DIRECTION, C>(rough, model, P, rec, counter, blocks, st);
 }
 
 template <bool R, int M>
@@ -321,12 +358,9 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         else          { if (ts.model == 0) GEN(false, 0); else if (ts.model == 1) GEN(false, 1); else if (ts.model == 2) GEN(false, 2); else GEN(false, 3); }
 #undef GEN
     } else {
-#define GO(RR, MM) le = (sink != SINK_DIRECTION ? launch_trace_t<RR, MM, SINK_RECORDS>(P, rec, counter, blocks, st) \
-                         : P.n_slots > 1 ? launch_trace_t<RR, MM, SINK_DIRECTION_BATCHED>(P, rec, counter, blocks, st) \
-                                         : launch_trace_t<RR, MM, SINK_DIRECTION>(P, rec, counter, blocks, st))
-        if (ts.rough) { if (ts.model == 0) GO(true, 0); else if (ts.model == 1) GO(true, 1); else if (ts.model == 2) GO(true, 2); else GO(true, 3); }
-        else          { if (ts.model == 0) GO(false, 0); else if (ts.model == 1) GO(false, 1); else if (ts.model == 2) GO(false, 2); else GO(false, 3); }
-#undef GO
+        const bool fast = ctx->contract == ALTB_CONTRACT_FAST && ts.model <= 1;      // other models: exact instances only
+        le = fast ? launch_trace_c<CONTRACT_FAST>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
+                  : launch_trace_c<CONTRACT_EXACT>(sink, ts.rough, ts.model, P, rec, counter, blocks, st);
     }
     ctx->launches++;
     ctx->trace_launches++;
@@ -848,10 +882,10 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
 }
 
 // ---------------------------------------------------------------------------------- replay
-template <bool R, int M>
+template <bool R, int M, int C = CONTRACT_EXACT>
 static void launch_replay_t(const ReplayParams& P, const double* ray0, const float4* tape, const unsigned long long* off,
                             const uint32_t* order, altb_record* rec, cudaStream_t st) {
-    k_replay<R, M><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, order, rec);
+    k_replay<R, M, C><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, order, rec);
 }
 
 extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
@@ -903,7 +937,12 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
         }
         const float4* t4 = reinterpret_cast<const float4*>(d_tape);
         cudaEventRecord(d.ev[0], d.stream);
-        if (rough) {
+        if (ctx->contract == ALTB_CONTRACT_FAST && model <= 1) {
+            if (rough) { if (model == 0) launch_replay_t<true, 0, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+                         else launch_replay_t<true, 1, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
+            else       { if (model == 0) launch_replay_t<false, 0, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+                         else launch_replay_t<false, 1, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
+        } else if (rough) {
             if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
             else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
             else if (model == 2) launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
@@ -960,7 +999,10 @@ extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, u
     CK(cudaSetDevice(d.dev));
     float* buf = nullptr;
     CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
-    k_draws<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
+    if (ctx->contract == ALTB_CONTRACT_FAST)
+        k_draws<CONTRACT_FAST><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
+    else
+        k_draws<CONTRACT_EXACT><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out, buf, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);

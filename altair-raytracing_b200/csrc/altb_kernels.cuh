@@ -40,7 +40,7 @@ static constexpr int ST_CROSSING = 100;
 // DEFER_CROSSING is the hot loop of k_trace: the ray is on the inner sphere by construction (s.where is not looked at),
 // everything that involves the port edge happens in the kernel's slow path.
 // zcf = the port plane R1 cos(theta_max) of the ray's scene (k.zc for single-scene launches; per lane in batched ones).
-template <bool ROUGH, int MODEL, bool DEFER_CROSSING>
+template <bool ROUGH, int MODEL, bool DEFER_CROSSING, int C = CONTRACT_EXACT>
 __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, float zcf, const DrawTabs& T, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
@@ -55,18 +55,18 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
     f3 d;
     float dn;
     if (MODEL == 0) {                  // Lambert: composed in the local frame of the true normal, d.nrm falls out
-        if (ROUGH) d = lambert_tilted(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, dr.u_r, dr.q_phi, dn);
-        else d = lambert_dir(T, nrm, dr.u_r, dr.q_phi, dn);
+        if (ROUGH) d = lambert_tilted<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, dr.u_r, dr.q_phi, dn);
+        else d = lambert_dir<C>(T, nrm, dr.u_r, dr.q_phi, dn);
     } else {
         f3 n = nrm;
-        if (ROUGH) tilt_normal(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n);
+        if (ROUGH) tilt_normal<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n);
         if (MODEL == 2) {
             float m = -2.0f * dot3(s.dir, n);
             d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
         } else if (MODEL == 3) {
             d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
         } else {
-            d = brdf_mix(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
+            d = brdf_mix<C>(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
         }
         dn = dot3(d, nrm);
     }
@@ -185,15 +185,15 @@ __device__ __noinline__ void exit_to_map(const TraceParams& P, uint32_t slot, fl
 // A ray on the port edge: bounce with the generic step until it is back on the inner sphere (returns 0) or ends
 // (returns the final status).  Out of line on purpose: it runs for 3e-4 of the surface hits and must not cost the hot
 // loop any registers.
-template <bool ROUGH, int MODEL>
+template <bool ROUGH, int MODEL, int C>
 __device__ __noinline__ int edge_bounces(const TraceParams& P, const Geom& g, const DrawTabs& T, uint32_t ctr_lo, RayState& t) {
     constexpr bool NEED_G = ROUGH || MODEL == 1;     // (T by reference: rebuilding it from trace_smem here measured 1.3 % slower)
     int st;
     do {
         HitDraws dr;
-        hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, t.hits, dr);
+        hit_from_philox<NEED_G, C>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, t.hits, dr);
         if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, t.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(g, P.k, (float)g.zc, T, t, dr);
+        st = bounce_step<ROUGH, MODEL, false, C>(g, P.k, (float)g.zc, T, t, dr);
     } while (st == 0 && t.where != EV_WALL);
     return st;
 }
@@ -201,7 +201,7 @@ __device__ __noinline__ int edge_bounces(const TraceParams& P, const Geom& g, co
 // The slow path of k_trace, out of line (one call per 32 port crossings): ptxas allocates the hot loop's registers without
 // seeing the double-precision code (inlined, the direction sink's acos / atan2 pushed the ray state of the bounce bodies
 // into local memory).  Entries q[0..take) are the crossings to resolve; resumed rays go to rq[nr..); returns the new nr.
-template <bool ROUGH, int MODEL, int SINK_>
+template <bool ROUGH, int MODEL, int SINK_, int C>
 __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const DrawTabs& T, altb_record* __restrict__ rec,
                                                  const QEntry* q, QEntry* rq, uint32_t take, uint32_t nr) {
     constexpr bool BATCHED = SINK_ == SINK_DIRECTION_BATCHED;
@@ -233,7 +233,7 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
             RayState t;
             t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
             t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
-            const int st = edge_bounces<ROUGH, MODEL>(P, g, T, P.ctr_lo0 + (id & imask), t);
+            const int st = edge_bounces<ROUGH, MODEL, C>(P, g, T, P.ctr_lo0 + (id & imask), t);
             if (st == ALTB_EXITED && SINK == SINK_DIRECTION) exit_to_map(P, slot, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
             else if (st) {
                 if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
@@ -256,7 +256,7 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
     return nr;
 }
 
-template <bool ROUGH, int MODEL, int SINK_>
+template <bool ROUGH, int MODEL, int SINK_, int C>
 __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constant__ TraceParams P,
                                                          altb_record* __restrict__ rec,
                                                          unsigned int* __restrict__ counter) {
@@ -349,9 +349,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             if (alive) {
                 HitDraws dr;
                 const uint32_t ctr_lo = P.ctr_lo0 + (BATCHED ? idx & imask : idx);
-                hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, s.hits, dr);
+                hit_from_philox<NEED_G, C>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, s.hits, dr);
                 if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, s.hits, P.k.lobe_n, P.k.lobe_ang);
-                const int st = bounce_step<ROUGH, MODEL, true>(P.g, P.k, BATCHED ? zc : P.k.zc, T, s, dr);
+                const int st = bounce_step<ROUGH, MODEL, true, C>(P.g, P.k, BATCHED ? zc : P.k.zc, T, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
                 else if (st) { finish(idx, s, st); alive = false; }
             }
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         if (nx >= 32 || (nx && !any_alive && exhausted && nr == 0)) {
             const uint32_t take = min(nx, 32u);
             nx -= take;
-            nr = drain_crossings<ROUGH, MODEL, SINK_>(P, T, rec, xq + nx, rq, take, nr);
+            nr = drain_crossings<ROUGH, MODEL, SINK_, C>(P, T, rec, xq + nx, rq, take, nr);
         }
     }
 
@@ -436,7 +436,7 @@ __global__ void k_fill_records(altb_record* rec, uint32_t n, altb_record proto) 
 // ------------------------------------------------------------------------------------ K1r replay
 struct ReplayParams { Geom g; KConsts k; uint32_t n; const float2* sincos; };
 
-template <bool ROUGH, int MODEL>
+template <bool ROUGH, int MODEL, int C>
 __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayParams P,
                                                 const double* __restrict__ ray0,
                                                 const float4* __restrict__ tape,
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
         HitDraws h;
         hit_from_draws(dr, P.k.rho, P.k.p_spec, h);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, T, s, h);
+        st = bounce_step<ROUGH, MODEL, false, C>(P.g, P.k, P.k.zc, T, s, h);
     }
     store_record(rec, i, s, st);
 }
@@ -944,13 +944,14 @@ __global__ void k_make_sincos_table(float2* __restrict__ tab) {
 }
 
 // ------------------------------------------------------------------------------------ RNG probe
+template <int C>
 __global__ void k_draws(const __grid_constant__ PhiloxKeys K, const float2* __restrict__ sincos, uint64_t ray_id0, uint32_t n, uint32_t k,
                         int lobe_n, float lobe_ang, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const DrawTabs T = make_tabs(sincos);
     Draws d;
-    make_draws<true>(K, T, ray_id0 + i, k, d);
+    make_draws<true, C>(K, T, ray_id0 + i, k, d);
     if (lobe_n > 0) d.u_r = lobe_accept(K, ray_id0 + i, k, lobe_n, lobe_ang);
     float4* o = reinterpret_cast<float4*>(out + 8 * (size_t)i);
     o[0] = make_float4(d.u_abs, d.u_r, d.u_phi, d.u_sel);

@@ -92,6 +92,18 @@ int  altb_device_count(void);
  * per-ray results), 2^32 / n_scenes where it bins in the kernel (DIRECTION maps: nothing is stored per ray). */
 int  altb_set_batch(altb_ctx* ctx, uint64_t batch_rays);
 
+/* Arithmetic contract of the bounce loop.
+ * ALTB_CONTRACT_EXACT (default): every FP32 result is an IEEE-754 correctly rounded operation or a table entry; the kernels
+ *   equal the CPU oracle bit for bit (what the parity suite checks).
+ * ALTB_CONTRACT_FAST: the same algorithm and the same random integers, with sqrt / reciprocal / log / sin / cos taken
+ *   straight from the GPU's special-function unit (relative error ~1e-7).  Results agree with the exact contract the way
+ *   BASELINE.json's north star defines agreement: per-ray replay against the double-precision CPU path differs for
+ *   <= 1e-4 of the rays, maps agree statistically (chi^2/ndf ~ 1).  Built for brdf_kind 0 and 1 with lambertian = 1; other
+ *   scenes, rim-aimed sources and altb_trace_paths always use the exact contract. */
+enum { ALTB_CONTRACT_EXACT = 0, ALTB_CONTRACT_FAST = 1 };
+int altb_set_contract(altb_ctx* ctx, int contract);
+int altb_get_contract(const altb_ctx* ctx);
+
 /* THE HOT PATH.  For each scene: trace rays ray_id0 .. ray_id0+n_rays-1 (ray i's random stream
  * depends only on (seed, i)) and accumulate the flux map.  counts[n_scenes][n_theta*n_phi] is
  * theta-major like the CSV rows and is ADDED to.  BATCHED SCENES: in DIRECTION mode, scenes that differ only in

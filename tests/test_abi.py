@@ -77,7 +77,7 @@ def test_hot_loop_has_no_spills(altb):
     altb.build_library()
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_spills.py"), altb.library_path()],
                          capture_output=True, text=True, check=True).stdout
-    inside = {m.group(1): int(m.group(2)) for m in re.finditer(r"k_trace<(\d,\d,\d)>.*?: (\d+) in the bounce bodies", out)}
+    inside = {m.group(1): int(m.group(2)) for m in re.finditer(r"k_trace<(\d,\d,\d)>:.*?: (\d+) in the bounce bodies", out)}
     # <rough, model, sink>: Lambert / CustomMirror with roughness, sinks 0 records, 1 in-kernel direction map, 2 batched scenes
     want = {f"1,{m},{s}" for m in (0, 1) for s in (0, 1, 2)}
     assert set(inside) >= want, out

@@ -1,0 +1,123 @@
+"""The FAST arithmetic contract (altb_set_contract, include/altair_b200.h): same algorithm and random integers as the
+bit-exact default, special functions straight from the GPU's MUFU unit.  It is validated the way BASELINE.json's north
+star states correctness --
+
+  * replay: recorded initial rays + draws, GPU result against the DOUBLE-PRECISION CPU oracle per ray: status, port
+    flag and bin index equal except for <= 1e-4 of the rays;
+  * statistics: maps agree bin by bin within Poisson errors (chi^2/ndf ~ 1), port fraction within 0.1 % (3 sigma where
+    the sample is too small to resolve 0.1 %);
+
+plus what makes it the SAME path: integer draw fields bit-identical, Gaussian deviates within 2e-6, and the in-kernel
+direction sink equal to the record sink + map kernel bit for bit under the same contract.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SEED = 4357
+
+
+@pytest.fixture()
+def fast(ctx, altb):
+    ctx.set_contract(altb.CONTRACT_FAST)
+    assert ctx.contract == altb.CONTRACT_FAST
+    yield ctx
+    ctx.set_contract(altb.CONTRACT_EXACT)
+
+
+def test_contract_switch_and_draws(ctx, altb, oracle):
+    exact = ctx.draws(SEED, 1 << 33, 200_000, 5)
+    ctx.set_contract(altb.CONTRACT_FAST)
+    try:
+        f = ctx.draws(SEED, 1 << 33, 200_000, 5)
+    finally:
+        ctx.set_contract(altb.CONTRACT_EXACT)
+    # uniforms / azimuth fractions come from the same integer fields
+    assert np.array_equal(exact[:, :5].view(np.uint32), f[:, :5].view(np.uint32))
+    dg = np.abs(f[:, 5:7].astype(np.float64) - exact[:, 5:7])
+    assert dg.max() <= 2e-6 * max(1.0, np.abs(exact[:, 5:7]).max()), dg.max()
+    g = f[:, 5:7].astype(np.float64).ravel()
+    assert abs(g.mean()) < 4 / np.sqrt(g.size) and abs(g.var() - 1.0) < 0.01
+    with pytest.raises(altb.AltbError):
+        ctx.set_contract(7)
+    assert ctx.contract == altb.CONTRACT_EXACT
+    again = ctx.draws(SEED, 1 << 33, 1000, 5)
+    assert np.array_equal(again.view(np.uint32), exact[:1000].view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(theta_max=170.0), dict(theta_max=164.0, brdf_kind=1), dict(theta_max=170.0, roughness=0.0),
+                                dict(theta_max=170.0, brdf_kind=1, roughness=0.0, reflectance=1.0, max_bounces=10000, world_half=200.0)])
+def test_replay_against_double_precision_oracle_fast(fast, oracle, altb, kw):
+    """North-star replay criterion for the fast contract: <= 1e-4 of the rays differ from the FP64 oracle."""
+    n = 200_000
+    tape, off = oracle.make_tape(oracle.scene(**kw), oracle.source(), n, seed=2)
+    ray0 = np.tile(np.array([-60.0, 0.0, -75.0, 5.0, 0.0, 0.0]), (n, 1))
+    ref = oracle.replay(oracle.scene(**kw), ray0, tape, off, prec=oracle.F64)
+    g_rec, g_bin, g_port = fast.replay(altb.scene(**kw), ray0, tape, off, altb.map_spec(mode=altb.MAP_DIRECTION))
+    ref_port = oracle.port_flags(oracle.scene(**kw), ref)
+    om = oracle.map_spec(mode=oracle.MAP_DIRECTION)
+    ref_bin = np.array([oracle.lib().orc_direction_bin(C.byref(om), r["dir"].ctypes.data_as(C.POINTER(C.c_float)))
+                        if p else -1 for r, p in zip(ref, ref_port)], dtype=np.int32)
+    bad = (g_rec["status"] != ref["status"]) | (g_rec["n_hits"] != ref["n_hits"]) | (g_port.astype(bool) != ref_port) | (g_bin != ref_bin)
+    assert bad.mean() <= 1e-4, (kw, bad.mean())
+    same = ~bad
+    assert np.abs(g_rec["dir"][same] - ref["dir"][same]).max() < 2e-4       # unit vectors: end directions agree to FP32 noise
+
+
+@pytest.mark.parametrize("kw", [dict(theta_max=170.0), dict(theta_max=170.0, brdf_kind=1)])
+def test_fast_trace_against_exact_trace_per_ray(ctx, altb, kw):
+    """Same ray ids under both contracts: the Gaussian deviates differ in the last bits, so a few trajectories part at a
+    boundary; everything else ends in the same state within FP32 noise."""
+    n = 400_000
+    e_rec, e_st = ctx.trace_records(altb.scene(**kw), altb.source(), n, seed=SEED)
+    ctx.set_contract(altb.CONTRACT_FAST)
+    try:
+        f_rec, f_st = ctx.trace_records(altb.scene(**kw), altb.source(), n, seed=SEED)
+    finally:
+        ctx.set_contract(altb.CONTRACT_EXACT)
+    bad = (e_rec["status"] != f_rec["status"]) | (e_rec["n_hits"] != f_rec["n_hits"])
+    assert bad.mean() <= 3e-4, bad.mean()
+    ok = ~bad
+    assert np.abs(e_rec["dir"][ok] - f_rec["dir"][ok]).max() < 5e-4
+    assert abs(e_st["n_bounces"] - f_st["n_bounces"]) <= 3e-4 * e_st["n_bounces"]
+
+
+def test_fast_statistics_against_independent_exact_run(ctx, altb):
+    """Statistical mode of the north star: INDEPENDENT samples (different ray ids) under the two contracts; every bin within
+    Poisson errors (chi^2/ndf ~ 1, max |z| < 5.5 over ~14 000 populated bins), port fraction within 0.1 %."""
+    n = 200_000_000
+    sc, src, mp = altb.scene(theta_max=170.0, brdf_kind=1), altb.source(), altb.map_spec(mode=altb.MAP_DIRECTION)
+    e_counts, e_st = ctx.trace_fluxmap(sc, src, n, mp, seed=SEED, ray_id0=0)
+    ctx.set_contract(altb.CONTRACT_FAST)
+    try:
+        f_counts, f_st = ctx.trace_fluxmap(sc, src, n, mp, seed=SEED, ray_id0=n)
+    finally:
+        ctx.set_contract(altb.CONTRACT_EXACT)
+    a, b = e_counts[0].astype(np.float64), f_counts[0].astype(np.float64)
+    use = (a + b) >= 50
+    z = (a[use] - b[use]) / np.sqrt(a[use] + b[use])
+    chi2 = float((z ** 2).mean())
+    assert use.sum() > 12_000 and 0.94 < chi2 < 1.06 and np.abs(z).max() < 5.5, (use.sum(), chi2, np.abs(z).max())
+    pe, pf = e_st[0]["n_exit_port"] / n, f_st[0]["n_exit_port"] / n
+    assert abs(pf / pe - 1.0) < 1e-3, (pe, pf)                                # 3 sigma of the difference is 3e-4 here
+    be, bf = e_st[0]["n_bounces"] / n, f_st[0]["n_bounces"] / n
+    assert abs(bf / be - 1.0) < 5e-4
+
+
+def test_fast_sinks_agree_and_batched(fast, altb):
+    """Under one contract the in-kernel direction sink, the batched launch and the record sink + map kernel are the same
+    arithmetic: identical integer maps."""
+    n = 300_000
+    mp = altb.map_spec(mode=altb.MAP_DIRECTION)
+    thetas = (160.0, 170.0, 175.0)
+    scenes = [altb.scene(theta_max=t, brdf_kind=1) for t in thetas]
+    b_counts, b_st = fast.trace_fluxmap(scenes, altb.source(), n, mp, seed=SEED)
+    for i, sc in enumerate(scenes):
+        s_counts, s_st = fast.trace_fluxmap(sc, altb.source(), n, mp, seed=SEED)
+        rec, r_st = fast.trace_records(sc, altb.source(), n, seed=SEED)
+        m_counts = fast.map_records(sc, mp, rec)
+        assert np.array_equal(b_counts[i], s_counts[0]) and np.array_equal(s_counts[0], m_counts)
+        for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+            assert b_st[i][key] == s_st[0][key] == r_st[key], key

@@ -26,6 +26,7 @@ ap.add_argument("--rays", type=int, default=100_000_000)
 ap.add_argument("--out", default="")
 ap.add_argument("--shard", choices=["rays", "scenes"], default="rays",
                 help="N>1: split every scene's rays over the ranks, or deal whole scenes round-robin (measured on 8 B200: 0.448 s vs 0.454 s)")
+ap.add_argument("--contract", default="fast", choices=["exact", "fast"])
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -33,6 +34,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 thetas = [100.0 + 0.5 * k for k in range(a.scenes)]
 ctx = A.Context([local])
+ctx.set_contract(A.CONTRACT_FAST if a.contract == "fast" else A.CONTRACT_EXACT)
 tr = ShardedTracer(ctx, [A.scene(theta_max=t) for t in thetas], A.source(), A.map_spec(mode=A.MAP_DIRECTION), device=local, shard=a.shard)
 tr.step(min(a.rays, 1_000_000))                      # warm-up
 torch.cuda.synchronize()
@@ -53,7 +55,7 @@ if rank == 0:
         rows.append({"theta_max": t, "escape_fraction": int(st[2]) / int(st[0]), "thin_wall_formula": 0.99 * f / (1 - 0.99 * (1 - f)),
                      "bounces_per_ray": int(st[5]) / int(st[0]), "map_sum": int(c.sum())})
     tot_b = int(stats[:, 5].sum()); tot_r = int(stats[:, 0].sum())
-    summary = {"workload": "C5 port-angle sweep", "n_gpus": world, "shard": a.shard if world > 1 else "none", "scenes": a.scenes, "rays_per_scene": a.rays, "seconds": ms.item() * 1e-3,
+    summary = {"workload": "C5 port-angle sweep", "contract": a.contract, "n_gpus": world, "shard": a.shard if world > 1 else "none", "scenes": a.scenes, "rays_per_scene": a.rays, "seconds": ms.item() * 1e-3,
                "rays_per_s": tot_r / (ms.item() * 1e-3), "ray_bounces_per_s": tot_b / (ms.item() * 1e-3), "total_bounces": tot_b}
     print(json.dumps(summary))
     for r in rows[::16]:

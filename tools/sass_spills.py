@@ -41,6 +41,6 @@ for name, ins in funcs.items():
         hot = (big[0][0], big[n_unrolled - 1][0] + body)
     loc = [(a, t) for a, t in ins if re.search(r"\b(STL|LDL)", t)]
     inside = [a for a, t in loc if hot[0] <= a <= hot[1]]
-    tag = re.search(r"k_traceILb(\d)ELi(\d)ELi(\d)", name)
-    print(f"k_trace<{tag.group(1)},{tag.group(2)},{tag.group(3)}>: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
+    tag = re.search(r"k_traceILb(\d)ELi(\d)ELi(\d)ELi(\d)", name)
+    print(f"k_trace<{tag.group(1)},{tag.group(2)},{tag.group(3)}>{'' if tag.group(4) == '0' else ' fast'}: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
           f"local-memory instructions: {len(inside)} in the bounce bodies, {len(loc) - len(inside)} elsewhere")
