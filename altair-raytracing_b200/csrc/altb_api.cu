@@ -102,7 +102,7 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     k.abs_thr = fa >= 16777216.0 ? 0xffffffffu : (((uint32_t)fa << 8) | 0xffu);
     k.spec_thr = (uint32_t)ceil((double)k.p_spec * 16384.0);
     // Box-Muller radius of a 20-bit u1: |g| <= sqrt(2 * 20 ln 2) = 5.2655
-    k.tilt_small = fabs((double)k.sigma) * 5.2656 <= (double)SINCOS_DIRECT_MAX;
+    k.tilt_small = fabs((double)k.sigma) * 5.2656 <= (double)SINCOS_TINY_MAX ? 2 : (fabs((double)k.sigma) * 5.2656 <= (double)SINCOS_DIRECT_MAX ? 1 : 0);
     k.spec_small = fabs((double)k.brdf_s) * 5.2656 <= (double)SINCOS_DIRECT_MAX;
     return 0;
 }

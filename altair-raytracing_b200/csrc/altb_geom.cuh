@@ -23,7 +23,7 @@ struct Geom {
 
 struct KConsts {
     float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n;
-    int tilt_small, spec_small;   // sigma * max|g| <= 0.9 / brdf_s * max|g| <= 0.9: sin/cos without the quadrant reduction
+    int tilt_small, spec_small;   // sigma * max|g| <= 0.9 / brdf_s * max|g| <= 0.9: sin/cos without the quadrant reduction (tilt_small = 2: <= 0.06)
     uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
 };
 

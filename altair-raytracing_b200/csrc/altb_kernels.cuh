@@ -55,11 +55,11 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
     f3 d;
     float dn;
     if (MODEL == 0) {                  // Lambert: composed in the local frame of the true normal, d.nrm falls out
-        if (ROUGH) d = lambert_tilted<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, dr.u_r, dr.q_phi, dn);
+        if (ROUGH) d = lambert_tilted<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small, dr.u_r, dr.q_phi, dn);
         else d = lambert_dir<C>(T, nrm, dr.u_r, dr.q_phi, dn);
     } else {
         f3 n = nrm;
-        if (ROUGH) tilt_normal<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small != 0, n);
+        if (ROUGH) tilt_normal<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small, n);
         if (MODEL == 2) {
             float m = -2.0f * dot3(s.dir, n);
             d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
@@ -282,20 +282,34 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
     RayState s;
     s.pos = {0.f, 0.f, 0.f}; s.dir = {0.f, 0.f, 0.f}; s.hits = 0; s.where = EV_WALL;
 
-    auto finish = [&](uint32_t id, const RayState& t, int st) {      // a ray that ended on the wall / edge (absorbed, suspended)
-        const uint32_t slot = BATCHED ? id >> shift : 0u;
-        if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
-        else {       // absorbed rays are not counted one by one: absorbed = rays - exited - suspended (k_reduce_trace_stats)
-            unsigned long long* gs = trace_stats(P, BATCHED ? P.n_slots : 1u, slot);
-            if (st == ALTB_ABSORBED) atomicAdd(gs + 4, (unsigned long long)t.hits);
-            else stat_end(gs, 3, t.hits);
-        }
-    };
+    // SINK_DIRECTION: a ray that ends on the wall (absorbed / suspended) costs the bounce body NOTHING: the dead lane keeps its
+    // hit count (bit 31 = suspended) and the next regeneration accounts for all dead lanes of the warp at full width --
+    // single scene: one REDUX + one ballot, lane 0 adds the warp's sums to the block's statistics (RED.64);
+    // batched: one RED.64 per ended ray into its slot.  Absorbed rays are not counted at all: absorbed = rays - exited -
+    // suspended (k_reduce_trace_stats).  (Done in the bounce body, ptxas if-converts the accounting: ~7 predicated
+    // instructions per surface hit for an event that happens once per ray.)
 
     while (true) {
         // ---- regeneration
         unsigned need = __ballot_sync(FULL, !alive);
         if (need) {
+            if (SINK == SINK_DIRECTION) {               // account for the rays that ended since the last check
+                const uint32_t hraw = alive ? 0u : s.hits;
+                if (!BATCHED) {
+                    const uint32_t tot = __reduce_add_sync(FULL, hraw & 0x7fffffffu);
+                    const uint32_t nsus = __popc(__ballot_sync(FULL, (hraw >> 31) != 0u));
+                    if (lane == 0 && tot) {             // (no shared-memory accumulator + flush at the end: any code after
+                        unsigned long long* gs = trace_stats(P, 1u, 0u);    //  the loop made ptxas spill inside the bounce bodies)
+                        atomicAdd(gs + 4, (unsigned long long)tot);
+                        if (nsus) atomicAdd(gs + 3, (unsigned long long)nsus);
+                    }
+                } else if (hraw) {
+                    unsigned long long* gs = trace_stats(P, P.n_slots, idx >> shift);
+                    atomicAdd(gs + 4, (unsigned long long)(hraw & 0x7fffffffu));
+                    if (hraw >> 31) atomicAdd(gs + 3, 1ull);
+                }
+                if (!alive) s.hits = 0;
+            }
             if (nr) {                                   // resume parked rays first
                 const uint32_t rank = __popc(need & lt_mask);
                 if (!alive && rank < nr) {
@@ -339,13 +353,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         if (!any_alive && exhausted && nx == 0 && nr == 0) break;
 
         // ---- ALTB_BOUNCES_PER_CHECK surface hits per live lane between two regeneration checks
+        bool crossing = false;
 #if ALTB_BPC_UNROLL
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
         for (int rep = 0; rep < ALTB_BOUNCES_PER_CHECK; rep++) {
-            bool crossing = false;
             if (alive) {
                 HitDraws dr;
                 const uint32_t ctr_lo = P.ctr_lo0 + (BATCHED ? idx & imask : idx);
@@ -353,8 +367,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                 if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, s.hits, P.k.lobe_n, P.k.lobe_ang);
                 const int st = bounce_step<ROUGH, MODEL, true, C>(P.g, P.k, BATCHED ? zc : P.k.zc, T, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
-                else if (st) { finish(idx, s, st); alive = false; }
+                else if (st) {
+                    if (SINK == SINK_RECORDS) store_record(rec, idx, s, st);
+                    else if (st == ALTB_SUSPENDED) s.hits |= 0x80000000u;
+                    alive = false;
+                }
             }
+        }
+        // ---- park the pass's port crossings (a crossing lane is dead for the rest of the pass and keeps its state): one
+        //      ballot per pass, not per surface hit
+        {
             const unsigned cm = __ballot_sync(FULL, crossing);
             if (cm) {
                 if (crossing) {
@@ -362,6 +384,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
                     e.b = make_float4(s.dir.y, s.dir.z, __uint_as_float(idx), __uint_as_float(s.hits));
                     xq[nx + __popc(cm & lt_mask)] = e;
+                    if (SINK == SINK_DIRECTION) s.hits = 0;        // the hit count travels with the queue entry
                 }
                 nx += __popc(cm);
                 __syncwarp();

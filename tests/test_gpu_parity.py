@@ -233,8 +233,10 @@ def test_batched_scenes_160_and_mixed_groups(ctx, oracle, altb):
     gm = altb.map_spec(mode=altb.MAP_DIRECTION)
     t0 = ctx.trace_launches
     g_counts, g_st = ctx.trace_fluxmap([altb.scene(theta_max=t) for t in thetas], altb.source(), n, gm, seed=11)
-    assert ctx.trace_launches - t0 == 1
-    for i in (0, 76, 77, 78, 100, 140, 159):
+    # 100 .. 137.5 deg: the beam leaves at once (no launch); 138.0 and 138.5 deg: its first event is the port rim (generic
+    # one-thread-per-ray tracer, one launch each); the other 81 scenes share one persistent launch
+    assert ctx.trace_launches - t0 == 3
+    for i in (0, 75, 76, 77, 78, 100, 140, 159):
         o_counts, o_st = _direction_oracle(oracle, dict(theta_max=thetas[i]), n, seed=11)
         assert np.array_equal(g_counts[i], o_counts), thetas[i]
         assert g_st[i]["n_bounces"] == o_st["n_bounces"] and g_st[i]["n_absorbed"] == o_st["n_absorbed"]

@@ -16,3 +16,11 @@ timeout 300 python tools/port_angle_sweep.py --out $out/${tag}_c5.json > $out/${
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu $BENCH_FLAGS > $out/${tag}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -o $out/${tag}_ktrace python tools/profile_case.py --rays 60000000 --reps 1 $PROFILE_FLAGS > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $out | tail -20
+for v in altair-raytracing_b200/variants/*.so; do
+  [ -f "$v" ] || continue
+  echo "variant $v" >> $out/${tag}_variants.log
+  for c in fast exact; do ALTB_LIB=$v timeout 120 python tools/profile_case.py --rays 200000000 --reps 2 --contract $c 2>&1 | tail -1 >> $out/${tag}_variants.log; done
+done
+echo "variant default" >> $out/${tag}_variants.log
+for c in fast exact; do timeout 120 python tools/profile_case.py --rays 200000000 --reps 2 --contract $c 2>&1 | tail -1 >> $out/${tag}_variants.log; done
+cat $out/${tag}_variants.log
