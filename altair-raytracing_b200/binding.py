@@ -126,6 +126,7 @@ def load_library():
                                       vp, P(Stats)]
     L.altb_replay.argtypes = [vp, P(Scene), vp, vp, vp, u64, P(MapSpec), vp, vp, vp]
     L.altb_map_records.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, vp]
+    L.altb_map_records_at.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, u64, vp]
     L.altb_probe_f32.argtypes = [vp, C.c_int, vp, u64, vp]
     L.altb_draws.argtypes = [vp, u64, u64, u64, u32, vp]
     L.altb_draws_lobe.argtypes = [vp, u64, u64, u64, u32, C.c_int, C.c_double, vp]
@@ -257,10 +258,11 @@ class Context:
                                         _ptr(bins) if mp is not None else None, _ptr(port)))
         return rec, bins, port
 
-    def map_records(self, sc, mp, rec):
+    def map_records(self, sc, mp, rec, ray_id0=0):
+        """Map stage alone; rec[i] is the ray with global id ray_id0 + i (matters for the per-position modes)."""
         rec = np.ascontiguousarray(rec)
         counts = np.zeros(mp.n_theta * mp.n_phi, dtype=np.uint64)
-        self._check(self._L.altb_map_records(self._h, C.byref(sc), C.byref(mp), _ptr(rec), len(rec), _ptr(counts)))
+        self._check(self._L.altb_map_records_at(self._h, C.byref(sc), C.byref(mp), _ptr(rec), ray_id0, len(rec), _ptr(counts)))
         return counts
 
     def draws(self, seed, ray_id0, n, k, lobe_n=0, lobe_deg=0.0):

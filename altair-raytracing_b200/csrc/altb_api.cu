@@ -807,8 +807,14 @@ extern "C" int altb_trace_exit_rays(altb_ctx* ctx, const altb_scene* scene, cons
 }
 
 // ---------------------------------------------------------------------------------- map on host records
+extern "C" int altb_map_records_at(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
+                                   const altb_record* records, uint64_t ray_id0, uint64_t n, uint64_t* counts);
 extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
                                 const altb_record* records, uint64_t n, uint64_t* counts) {
+    return altb_map_records_at(ctx, scene, map, records, 0, n, counts);
+}
+extern "C" int altb_map_records_at(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
+                                   const altb_record* records, uint64_t ray_id0, uint64_t n, uint64_t* counts) {
     if (!ctx || !scene || !map || (!records && n) || !counts) return fail(ALTB_E_ARG, "altb_map_records: NULL argument");
     DevCtx& d = ctx->devs[0];
     CK(cudaSetDevice(d.dev));
@@ -824,7 +830,7 @@ extern "C" int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const al
     for (uint64_t off = 0; off < n; off += batch) {
         const uint32_t m = (uint32_t)std::min<uint64_t>(batch, n - off);
         CK(cudaMemcpyAsync(d.rec, records + off, (size_t)m * sizeof(altb_record), cudaMemcpyHostToDevice, d.stream));
-        if (int rc = run_map(ctx, d, ms, d.rec, d.counter, m, off, d.counts, nullptr, nullptr, d.stream)) return rc;
+        if (int rc = run_map(ctx, d, ms, d.rec, d.counter, m, ray_id0 + off, d.counts, nullptr, nullptr, d.stream)) return rc;
     }
     std::vector<unsigned long long> host(nb);
     CK(cudaMemcpyAsync(host.data(), d.counts, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));

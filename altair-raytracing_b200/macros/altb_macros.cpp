@@ -88,6 +88,15 @@ altb_scene simpleScene(double thetaMax, double rOuter, double roughness) {
     return s;
 }
 
+// the block of ray ids of this macro call (Settings::next_ray_id)
+uint64_t takeRays(uint64_t n) {
+    Settings& S = settings();
+    const uint64_t first = S.next_ray_id;
+    if (S.advance_ray_ids) S.next_ray_id += n;
+    last_run().first_ray_id = first;
+    return first;
+}
+
 altb_source makeSource(double x, double y, double z, double dx, double dy, double dz) {
     altb_source s = {{x, y, z}, {dx, dy, dz}};
     return s;
@@ -258,7 +267,7 @@ void perPositionSweep(bool twofold, bool notify, const char* saveFolder, int thr
     altb_map_spec map = {nThetaBins, nPhiBins, 100 * cm, 40 * cm, twofold ? ALTB_MAP_TWOFOLD : ALTB_MAP_PER_POSITION, n};
     std::vector<uint64_t> counts((size_t)totalPositions, 0);
     altb_stats st;
-    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, 0, (uint64_t)runs * (uint64_t)n, S.seed, &map, counts.data(), &st) != 0) {
+    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, takeRays((uint64_t)runs * (uint64_t)n), (uint64_t)runs * (uint64_t)n, S.seed, &map, counts.data(), &st) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
     }
@@ -328,7 +337,7 @@ void fluxAtObserverFast::sweepDetectorTraceOnce(bool notify, const char* saveFol
     altb_map_spec map = {nThetaBins, nPhiBins, 100 * cm, 40 * cm, S.traceonce_as_shipped ? ALTB_MAP_TRACEONCE_COMPAT : ALTB_MAP_LINE, 0};
     std::vector<uint64_t> counts((size_t)nThetaBins * nPhiBins, 0);
     altb_stats st;
-    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, 0, (uint64_t)n, S.seed, &map, counts.data(), &st) != 0) {
+    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, takeRays((uint64_t)n), (uint64_t)n, S.seed, &map, counts.data(), &st) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
     }
@@ -409,7 +418,7 @@ void legacySweep(bool nonLambertian) {
         std::cout << "Format: theta(\xC2\xB0), phi(\xC2\xB0): hits/total = fraction" << std::endl;
         std::cout << "----------------------------------------" << std::endl;
     }
-    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, 0, (uint64_t)n * nThetaBins * nPhiBins, S.seed, &map, counts.data(), &st) != 0) {
+    if (altb_trace_fluxmap(ctx.h, &scene, 1, &src, takeRays((uint64_t)n * nThetaBins * nPhiBins), (uint64_t)n * nThetaBins * nPhiBins, S.seed, &map, counts.data(), &st) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
     }
@@ -449,7 +458,7 @@ void makeIntegratingSphereNRays() {
     altb_scene scene = simpleScene(170., 101 * cm, 0.0);
     altb_source src = makeSource(-60 * cm, 0 * cm, -80 * cm, 5, 0, 0);
     altb_stats st;
-    if (altb_trace_exit_rays(ctx.h, &scene, &src, 0, (uint64_t)n, settings().seed, nullptr, nullptr, nullptr, nullptr, &st) != 0) {
+    if (altb_trace_exit_rays(ctx.h, &scene, &src, takeRays((uint64_t)n), (uint64_t)n, settings().seed, nullptr, nullptr, nullptr, nullptr, &st) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
     }
@@ -500,7 +509,7 @@ void integratingSphereDetectorSweep() {
     std::vector<uint64_t> hits(m, 0);
     altb_stats st;
     // the reference re-traces nRays for every position; here one trace serves all positions
-    if (altb_detector_sweep(ctx.h, &scene, &src, 0, (uint64_t)nRays, S.seed, centers.data(), rots.data(), m, diskRadius, 0.1 * cm,
+    if (altb_detector_sweep(ctx.h, &scene, &src, takeRays((uint64_t)nRays), (uint64_t)nRays, S.seed, centers.data(), rots.data(), m, diskRadius, 0.1 * cm,
                             hits.data(), &st) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
@@ -530,7 +539,7 @@ void distributionSphereDetectorSweep() {
     altb_scene scene = simpleScene(170., 101 * cm, 0.0);
     altb_source src = makeSource(-60 * cm, 0 * cm, -80 * cm, 5, 0, 0);
     std::vector<double> pos((size_t)n * 3), dir((size_t)n * 3);
-    if (altb_trace_exit_rays(ctx.h, &scene, &src, 0, (uint64_t)n, settings().seed, pos.data(), dir.data(), nullptr, nullptr, nullptr) != 0) {
+    if (altb_trace_exit_rays(ctx.h, &scene, &src, takeRays((uint64_t)n), (uint64_t)n, settings().seed, pos.data(), dir.data(), nullptr, nullptr, nullptr) != 0) {
         std::cerr << "Error: " << altb_last_error() << std::endl;
         return;
     }
@@ -569,6 +578,8 @@ int altbm_set(const char* key, double v) {
     else if (k == "sweep_dtheta") S.sweep_dtheta = v;
     else if (k == "distribution_rays") S.distribution_rays = (int)v;
     else if (k == "nonlambertian_rays") S.nonlambertian_rays = (int)v;
+    else if (k == "next_ray_id") S.next_ray_id = (uint64_t)v;
+    else if (k == "advance_ray_ids") S.advance_ray_ids = (int)v;
     else if (k == "seed") S.seed = (uint64_t)v;
     else if (k == "traceonce_as_shipped") S.traceonce_as_shipped = (int)v;
     else if (k == "verbose") S.verbose = (int)v;
@@ -583,6 +594,8 @@ long long altbm_last_count(const char* what) {
     if (w == "totalHitRays") return r.totalHitRays;
     if (w == "exitedRays") return r.exitedRays;
     if (w == "n_bounces") return r.n_bounces;
+    if (w == "first_ray_id") return (long long)r.first_ray_id;
+    if (w == "next_ray_id") return (long long)settings().next_ray_id;
     return -1;
 }
 double altbm_last_hist(const char* name, int bin) {

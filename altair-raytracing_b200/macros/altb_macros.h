@@ -35,6 +35,12 @@ struct Settings {
     int nonlambertian_rays = 100000;  // nonLambertianFlux.C:311
     double sweep_dtheta = 0.5;        // integratingSphereDetectorSweep.C:126
     uint64_t seed = 4357;             // TRandom3 default seed
+    // The reference's gRandom keeps advancing from one macro call to the next, so repeated calls (the five repeats per port
+    // angle of sweepSeries, fluxAtObserverFast.C:1641-1673) are independent samples.  Here a ray's random stream is
+    // (seed, ray id): every macro call takes the next unused block of ray ids.  advance_ray_ids = 0 pins every call to
+    // next_ray_id (reproducible single calls).
+    uint64_t next_ray_id = 0;
+    int advance_ray_ids = 1;
     int traceonce_as_shipped = 1;     // 1: reproduce the published trace-once maps (line from the origin);
                                       // 0: the intended semantics (true final segment)
     int verbose = 1;
@@ -48,6 +54,7 @@ struct LastRun {
     TH2D* fluxMap = nullptr;
     TH1D* hAngularDist = nullptr; TH1D* hDirectionZ = nullptr;
     long long fluxCount = 0, totalHitRays = 0, exitedRays = 0, n_bounces = 0;
+    unsigned long long first_ray_id = 0;      // ray ids [first_ray_id, first_ray_id + rays traced) of the last call
     double rayTime = 0, sweepTime = 0, totalTime = 0;
 };
 LastRun& last_run();

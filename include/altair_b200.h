@@ -153,9 +153,13 @@ int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, cons
                 const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map,
                 altb_record* records, int32_t* bin, uint8_t* port);
 
-/* Map stage alone on caller-provided records (host). counts is added to. */
+/* Map stage alone on caller-provided records (host). counts is added to.  records[i] is the ray with global id ray_id0 + i:
+ * the grouped modes (PER_POSITION, TWOFOLD) derive the detector position from the ray id, so a shard or batch that does not
+ * start at ray 0 must say where it starts (altb_map_records assumes ray_id0 = 0). */
 int altb_map_records(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
                      const altb_record* records, uint64_t n, uint64_t* counts);
+int altb_map_records_at(altb_ctx* ctx, const altb_scene* scene, const altb_map_spec* map,
+                        const altb_record* records, uint64_t ray_id0, uint64_t n, uint64_t* counts);
 
 /* Counter-based RNG exposed for verification: the 8 draws of hit k for rays ray_id0..+n-1. out[n][8]. */
 int altb_draws(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, uint32_t k, float* out);

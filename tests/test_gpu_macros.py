@@ -27,6 +27,8 @@ def M(altb, tmp_path_factory):
     out = tmp_path_factory.mktemp("macros")
     L.altbm_set_output_dir(str(out).encode())
     L.altbm_set(b"verbose", 0)
+    L.altbm_set(b"advance_ray_ids", 0)        # the oracle comparisons below trace ray ids 0 .. n-1; see test_repeated_calls_*
+    L.altbm_last_count.argtypes = [C.c_char_p]
     L.out = str(out)
     return L
 
@@ -54,6 +56,31 @@ def test_sweepDetectorTraceOnce(M, oracle):
     assert path.endswith("_1.csv")
     M.altbm_set(b"traceonce_as_shipped", 1)
     M.altbm_set(b"traceonce_rays", 100000)
+
+
+def test_repeated_calls_are_independent_samples(M, oracle):
+    """The reference's gRandom keeps advancing: the five repeats per port angle of sweepSeries (fluxAtObserverFast.C:1641-1673)
+    are independent samples.  With advance_ray_ids = 1 (the default) every macro call takes the next block of ray ids."""
+    n = 20000
+    M.altbm_set(b"traceonce_rays", n)
+    M.altbm_set(b"advance_ray_ids", 1)
+    M.altbm_set(b"next_ray_id", 0)
+    try:
+        maps = []
+        for rep in range(3):
+            M.altbm_sweepDetectorTraceOnce(0, b"rep", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+            assert M.altbm_last_count(b"first_ray_id") == rep * n
+            rows = _rows(M.altbm_last_csv().decode())
+            counts, _ = oracle.fluxmap(oracle.scene(theta_max=170.0), oracle.source(), n, oracle.map_spec(mode=oracle.MAP_TRACEONCE_COMPAT),
+                                       seed=4357, ray_id0=rep * n, prec=oracle.F32)
+            assert np.array_equal(np.rint(rows[:, 2] * n).astype(np.uint64), counts)
+            maps.append(rows[:, 2])
+        assert M.altbm_last_count(b"next_ray_id") == 3 * n
+        assert not np.array_equal(maps[0], maps[1]) and not np.array_equal(maps[1], maps[2])
+    finally:
+        M.altbm_set(b"advance_ray_ids", 0)
+        M.altbm_set(b"next_ray_id", 0)
+        M.altbm_set(b"traceonce_rays", 100000)
 
 
 def test_sweepDetector_per_position_and_twofold(M, oracle):

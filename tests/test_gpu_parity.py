@@ -485,7 +485,12 @@ def test_map_stage_alone_on_host_records(ctx, oracle, altb):
             assert np.array_equal(g, o), mode
         gm = altb.map_spec(20, 10, 100.0, 40.0, altb.MAP_PER_POSITION, rays_per_position=125)
         om = oracle.map_spec(20, 10, 100.0, 40.0, oracle.MAP_PER_POSITION, rays_per_position=125)
-        assert np.array_equal(ctx.map_records(sc_g, gm, rec), oracle.map_records(sc_o, om, rec, prec=oracle.F32))
+        whole = ctx.map_records(sc_g, gm, rec)
+        assert np.array_equal(whole, oracle.map_records(sc_o, om, rec, prec=oracle.F32))
+        # a shard that does not start at ray 0 says so (altb_map_records_at): the two halves add up to the whole map
+        cut = 12_345
+        parts = ctx.map_records(sc_g, gm, rec[:cut]) + ctx.map_records(sc_g, gm, rec[cut:], ray_id0=cut)
+        assert np.array_equal(parts, whole) and whole.sum() > 0
     finally:
         ctx.set_batch(0)
     assert ctx.map_records(sc_g, altb.map_spec(mode=altb.MAP_LINE), rec[:0]).sum() == 0

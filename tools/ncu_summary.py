@@ -1,6 +1,10 @@
 #!/usr/bin/env python
 """Print the metrics profiles/*.md quote from an ncu report as a markdown table:
-  python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-regex]"""
+  python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-regex]
+  python tools/ncu_summary.py gpurun_out/x.ncu-rep k_trace --json "<capture command>" <bounces in the launch> > profiles/rNN_k_trace_ncu.json
+The JSON form is what bench.py attaches to its line as `roofline.profile_reference` (numbers of a committed capture with the
+capture's own configuration -- never re-labelled as measurements of the bench run)."""
+import json
 import csv
 import re
 import subprocess
@@ -26,6 +30,7 @@ smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio""".split()
 
 rep = sys.argv[1]
 pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
+as_json = len(sys.argv) > 3 and sys.argv[3] == "--json"
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -33,6 +38,32 @@ for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
     if pat and not pat.search(name):
         continue
+    if as_json:
+        def val(m):
+            return float(r[hdr.index(m)].replace(",", "")) if m in hdr and r[hdr.index(m)] not in ("", "n/a") else None
+        def byt(m):
+            v, u = val(m), units[hdr.index(m)] if m in hdr else ""
+            return None if v is None else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
+        bounces = float(sys.argv[5]) if len(sys.argv) > 5 else None
+        inst = val("smsp__inst_executed.sum")
+        dur, du = val("gpu__time_duration.sum"), units[hdr.index("gpu__time_duration.sum")]
+        dur_ms = dur * {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(du, 1)
+        out_ = {"kernel": name, "capture": sys.argv[4] if len(sys.argv) > 4 else "", "report": rep,
+                "duration_ms": dur_ms, "bounces_in_launch": bounces,
+                "warp_instructions": inst,
+                "warp_instructions_per_32_bounces": inst * 32 / bounces if bounces else None,
+                "active_lanes_per_instruction": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "issue_slots_busy_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fma_pipe_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                "alu_pipe_pct": val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "xu_pipe_pct": val("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                "lsu_pipe_pct": val("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct": val("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "dram_bytes_per_launch": (byt("dram__bytes_read.sum") or 0) + (byt("dram__bytes_write.sum") or 0),
+                "registers_per_thread": val("launch__registers_per_thread"), "grid": val("launch__grid_size"),
+                "block": val("launch__block_size")}
+        print(json.dumps(out_, indent=1))
+        break
     print(f"## {name}\n\n| metric | unit | value |\n|---|---|---|")
     for w in WANT:
         if w in hdr:
