@@ -44,7 +44,7 @@ struct DevCtx {
     unsigned long long* gstat[2] = {nullptr, nullptr};  // k_trace's per-block statistics (direction sink), same
     unsigned long long* stats_scratch = nullptr; uint64_t stats_scratch_cap = 0;
     // LINE-map tables of the last map spec (setup_map)
-    bool map_cached = false; altb_map_spec map_key; MapParams map_M; int map_n_tiles = 0; size_t map_line_smem = 0;
+    bool map_cached = false; altb_map_spec map_key; MapParams map_M; int map_n_tiles = 0; size_t map_line_smem = 0, map_rect_smem = 0;
     std::vector<float> tab_host; std::vector<float4> tiles_host;
     double* dirtab = nullptr; uint64_t dirtab_cap = 0; int dir_nt = 0, dir_np = 0; std::vector<double> dirtab_host;    // direction_bin edges
     cudaStream_t aux[2] = {nullptr, nullptr};
@@ -167,8 +167,8 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         d.dev = dev;        // from here on altb_destroy frees whatever this device already owns
         if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&d.counter, sizeof(unsigned int)) != cudaSuccess ||
-            cudaMalloc(&d.counter2, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&d.counter, 4 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&d.counter2, 4 * sizeof(unsigned int)) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.aux[0], cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.aux[1], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming) != cudaSuccess ||
@@ -380,7 +380,7 @@ static inline uint64_t piece_len(uint64_t ray_id, uint64_t left, uint64_t cap) {
 }
 
 // ---------------------------------------------------------------------------------- map setup
-struct MapSetup { MapParams M; int n_tiles; size_t line_smem; size_t dir_smem; };
+struct MapSetup { MapParams M; int n_tiles; size_t line_smem; size_t dir_smem; size_t rect_smem; };
 
 static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom& g, const KConsts& k, const altb_map_spec* map,
                      MapSetup& ms, cudaStream_t st) {
@@ -401,7 +401,7 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     ms.dir_smem = (size_t)nt * np * sizeof(unsigned int);
     M.use_smem_hist = ms.dir_smem <= 160 * 1024;
     if (!M.use_smem_hist) ms.dir_smem = 0;
-    ms.n_tiles = 0; ms.line_smem = 0;
+    ms.n_tiles = 0; ms.line_smem = 0; ms.rect_smem = 0;
     if (map->map_mode == ALTB_MAP_DIRECTION) {
         // bin edges of direction_bin: cos(i w_theta), i = 0..n_theta; (cos, sin)(j w_phi), j = 0..n_phi (the last one = the first)
         if (d.dir_nt != nt || d.dir_np != np) {
@@ -430,7 +430,8 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
         M.t_theta = d.map_M.t_theta; M.t_phi = d.map_M.t_phi; M.nt_theta = d.map_M.nt_theta; M.nt_phi = d.map_M.nt_phi;
         M.rs = d.map_M.rs; M.pz = d.map_M.pz; M.st = d.map_M.st; M.ct = d.map_M.ct; M.cp = d.map_M.cp; M.sp = d.map_M.sp;
         M.tiles = d.map_M.tiles; M.supers = d.map_M.supers;
-        ms.n_tiles = d.map_n_tiles; ms.line_smem = d.map_line_smem;
+        M.row4 = d.map_M.row4; M.col2 = d.map_M.col2; M.det_R = d.map_M.det_R; M.det_W = d.map_M.det_W;
+        ms.n_tiles = d.map_n_tiles; ms.line_smem = d.map_line_smem; ms.rect_smem = d.map_rect_smem;
         return 0;
     }
     if (d.map_cached) { CK(cudaDeviceSynchronize()); d.map_cached = false; }     // kernels of an earlier call may still read the old tables
@@ -512,6 +513,11 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     ms.line_smem = (size_t)LINE_BATCH * 2 * sizeof(float4) + (size_t)ms.n_tiles * LINE_WORDS * sizeof(uint32_t) +
                    (size_t)(ms.n_tiles + nst * nsp) * sizeof(float4) + (size_t)nst * nsp * sizeof(uint32_t) + ((size_t)4 * nt + 2 * np) * sizeof(float);
     if (ms.line_smem > 200 * 1024) return fail(ALTB_E_ARG, "map: %d x %d bins need %zu B of shared memory", nt, np, ms.line_smem);
+    // packed copies for the ray-stationary kernel: (rs, pz, st, ct) per row, (cp, sp) per column, 16-byte aligned behind the flat tables
+    const size_t flat = ((size_t)4 * nt + 2 * np + 3) & ~(size_t)3;
+    tab.resize(flat + (size_t)4 * nt + 2 * np);
+    for (int i = 0; i < nt; i++) for (int c = 0; c < 4; c++) tab[flat + 4 * i + c] = tab[(size_t)c * nt + i];
+    for (int j = 0; j < np; j++) { tab[flat + 4 * nt + 2 * j] = tab[4 * nt + j]; tab[flat + 4 * nt + 2 * j + 1] = tab[4 * nt + np + j]; }
     if (int rc = ensure(d.tables, d.tables_cap, (uint64_t)tab.size())) return rc;
     if (int rc = ensure(d.tiles, d.tiles_cap, (uint64_t)best_tiles.size())) return rc;
     CK(cudaMemcpyAsync(d.tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -519,7 +525,10 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     M.rs = d.tables; M.pz = d.tables + nt; M.st = d.tables + 2 * nt; M.ct = d.tables + 3 * nt;
     M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
     M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
-    d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_cached = true;
+    M.row4 = reinterpret_cast<const float4*>(d.tables + flat); M.col2 = reinterpret_cast<const float2*>(d.tables + flat + 4 * nt);
+    M.det_R = (float)map->det_radius; M.det_W = (float)(hw + 0.5);
+    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)nt * sizeof(float4) + (size_t)4 * np * sizeof(float);
+    d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_rect_smem = ms.rect_smem; d.map_cached = true;
     return 0;
 }
 
@@ -558,14 +567,32 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const altb_reco
         CK(cudaGetLastError());
         return 0;
     }
+    // ---- LINE / TRACEONCE_COMPAT: escaping rays -> test lines (+ candidate rectangles) -> ray-stationary kernel, the rest by tiles
     CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;
-    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (int rc = ensure(d.lines, d.lines_cap, 4 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;      // two lists of 2 float4 per ray
+    float4* lines_r = d.lines;
+    float4* lines_t = d.lines + 2 * (size_t)std::max<uint64_t>(d.rec_cap, n);
+    MapParams Mp = M;
+    const bool rect_ok = ms.rect_smem <= 200 * 1024;
+    Mp.force_tiles = !rect_ok || getenv("ALTB_LINE_TILES") != nullptr;
+    CK(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));
     {
         int cb = d.sm_count * 8;
         const int need = (int)((n + 255) / 256);
         if (cb > need) cb = need;
-        k_compact_exits<<<cb, 256, 0, st>>>(rec, n, M, d.lines, counter);
+        k_prepare_lines<<<cb, 256, 0, st>>>(rec, n, Mp, lines_r, lines_t, counter);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (!Mp.force_tiles) {
+        if (ms.rect_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_map_line_rect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line_rect, RECT_THREADS, ms.rect_smem));
+        if (per_sm < 1) per_sm = 1;
+        int blocks = d.sm_count * per_sm;
+        const int need = (int)((n + 8 * (RECT_THREADS / 32) - 1) / (8 * (RECT_THREADS / 32)));     // >= 8 rays per warp, or fewer blocks
+        if (blocks > need) blocks = std::max(need, 1);
+        k_map_line_rect<<<blocks, RECT_THREADS, ms.rect_smem, st>>>(lines_r, counter, Mp, d_counts);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -575,7 +602,7 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const altb_reco
     int blocks = d.sm_count * per_sm;
     const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
     if (blocks > need) blocks = need;
-    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(d.lines, counter, M, d_counts);
+    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(lines_t, counter + 1, Mp, d_counts);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -3,8 +3,9 @@
 //       k_trace_generic  one thread per ray, for sources whose first event is the port rim
 //   K1r k_replay       same state machine, draws streamed from a recorded tape
 //   K2a k_map_direction  records -> stats + one-bin-per-ray direction map (warp-compacted binning, shared-memory histogram)
-//   K2b k_compact_exits + k_map_line  records -> 16 200 overlapping line-disk tests per ray, culled by tiles,
-//                      bin-stationary register accumulation (no atomics in the inner loop)
+//   K2b k_prepare_lines + k_map_line_rect (ray-stationary: the cap of candidate bins as a (theta, phi) rectangle, packed
+//                      FP32 pair tests, shared-memory histogram) + k_map_line (tile-culled, bin-stationary; the rays whose
+//                      rectangle would be wasteful)  records -> 16 200 overlapping line-disk tests per ray
 //   K2c k_map_per_position, k_stats   K2d k_disk_hits (f32 pre-test + compacted FP64 tests)
 //       k_make_sincos_table, k_draws, k_probe_f32, k_fill_records, k_fma_peak
 // What they replace in the reference: ROBAST AOpticsManager::TraceNonSequential as called from
@@ -515,6 +516,10 @@ struct MapParams {
     int t_theta, t_phi, nt_theta, nt_phi;                                // tile shape / tile grid
     int use_smem_hist;
     const double* dir_tab;         // DIRECTION mode: bin edges (direction_bin)
+    int force_tiles;               // LINE modes: every ray to the tile kernel (ALTB_LINE_TILES=1, A/B measurements)
+    float det_R, det_W;            // LINE modes: detector-hemisphere radius; det_width / 2 + 0.5 cm of f32 slack (k_prepare_lines)
+    const float4* row4;            // LINE modes: (rs, pz, st, ct) per theta row, packed for one 128-bit load
+    const float2* col2;            // LINE modes: (cp, sp) per phi column
     int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
 };
 
@@ -685,36 +690,6 @@ static constexpr int LINE_WORDS = LINE_BATCH / 32;
 static constexpr int LINE_THREADS = ALTB_LINE_THREADS;
 static constexpr int SUPER = 4;             // a super-tile is SUPER x SUPER tiles
 
-// records -> dense list of the escaping rays' test lines (L.xyz, v.x | v.yz, 0, 0); order is irrelevant
-// (integer counts).  TRACEONCE_COMPAT: the line from the origin through the exit point (fluxAtObserverFast.C:1181).
-__global__ void __launch_bounds__(256) k_compact_exits(const altb_record* __restrict__ rec, uint32_t n, const MapParams M,
-                                                       float4* __restrict__ lines, unsigned int* __restrict__ n_lines) {
-    const unsigned lane = threadIdx.x & 31u;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        bool pf = false; f3 pos, dir; uint32_t hits, status;
-        if (i < n) {
-            load_record(rec, i, pos, dir, hits, status);
-            pf = port_flag(M.count_all, M.exit_zf, pos, status);
-        }
-        const unsigned m = __ballot_sync(FULL, pf);
-        unsigned base = 0;
-        if (lane == 0 && m) base = atomicAdd(n_lines, (unsigned)__popc(m));
-        base = __shfl_sync(FULL, base, 0);
-        if (pf) {
-            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-            f3 L, v;
-            if (M.mode == ALTB_MAP_TRACEONCE_COMPAT) {
-                const float inv = 1.0f / sqrtf(dot3(pos, pos));
-                L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
-            } else { L = pos; v = dir; }
-            lines[2 * (size_t)slot] = make_float4(L.x, L.y, L.z, v.x);
-            lines[2 * (size_t)slot + 1] = make_float4(v.y, v.z, 0.f, 0.f);
-        }
-    }
-}
-
 // dynamic shared memory layout:
 //   float4 rays[LINE_BATCH][2]; uint32 bitmap[n_tiles][LINE_WORDS]; float4 tiles[n_tiles]; float4 supers[n_super];
 //   uint32 sup_ij[n_super]; tables
@@ -816,6 +791,205 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
             }
             if (inb && acc) atomicAdd(counts + (size_t)i * M.n_phi + j, (unsigned long long)acc);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2b' ray-stationary line map
+// The detector centres a line can hit lie on the hemisphere of radius R about c0 = (0, 0, -100) AND within w of the line
+// (the hit point is on the line and at most w = det_width/2 from the centre).  For a line that pierces that sphere at P
+// with the chord half-length tp the candidates form a cap about P: writing a candidate as P + a v + w_perp (|w_perp| <= W),
+// |candidate - c0| = R gives a^2 + 2 tp a + q = 0 with q = 2 m.w_perp + |w_perp|^2 in [-2hW, 2hW + W^2] (m = foot of the
+// perpendicular from c0, h = |m|), so |a| <= tp - sqrt(tp^2 - 2hW - W^2) and the chord radius of the cap is
+// sqrt(W^2 + a_max^2).  The cap's (theta, phi) bounding rectangle holds 2.2 x the bins that are actually hit (640 vs 290 at
+// theta_max = 170 deg; the tile culling of k_map_line tests 2.8 x, after ~500 instructions of culling per ray).
+// k_prepare_lines computes the rectangle(s) of every escaping ray, one ray per lane; rays whose rectangles would be wasteful
+// (grazing lines of the TRACEONCE_COMPAT semantics, lines that miss the sphere, overlapping caps) go to the tile kernel.
+// k_map_line_rect is ray-stationary: a warp takes one ray at a time and tests the rectangle 64 bins per pass -- each lane
+// two neighbouring phi bins of one row with packed FP32 (FMUL2 / FFMA2 / FADD2: the same IEEE results as line_hit, 30
+// instead of 48 instructions per pair) -- and hits go to a per-block shared-memory histogram with shared atomics.
+struct LineRect { int i0, ni, j0, nj; };            // rows i0 .. i0+ni-1, columns (j0 + 0 .. nj-1) mod n_phi
+__device__ __forceinline__ uint32_t pack_rect(const LineRect& r) { return (uint32_t)r.i0 | (uint32_t)r.ni << 8 | (uint32_t)r.j0 << 16 | (uint32_t)r.nj << 24; }
+__device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 255u), (int)(u >> 8 & 255u), (int)(u >> 16 & 255u), (int)(u >> 24)}; }
+static constexpr int RECT_MAX_BINS = 4096;          // larger rectangles: the tile kernel culls better
+static constexpr int RECT_MAX_DIM = 255;            // 8-bit fields
+
+// (theta, phi) bounding rectangle of the cap of angular radius alpha (sin / cos given) about the unit direction u (relative
+// to c0, z up): false if no bin centre of the lower hemisphere can lie in it
+__device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy, float uz, float alpha, LineRect& r) {
+    const float HALF_PI = 1.5707964f;
+    const float thc = acosf(fminf(fmaxf(-uz, -1.0f), 1.0f));
+    const float tlo = thc - alpha, thi = thc + alpha;
+    if (tlo >= HALF_PI) return false;
+    const float inv_dth = (float)M.n_theta * (1.0f / HALF_PI);
+    int i0 = (int)ceilf(tlo * inv_dth - 0.5f - 1e-3f), i1 = (int)floorf(thi * inv_dth - 0.5f + 1e-3f);
+    i0 = max(i0, 0); i1 = min(i1, M.n_theta - 1);
+    if (i1 < i0) return false;
+    int j0 = 0, nj = M.n_phi;
+    const float sa = sinf(alpha), sc = sinf(thc);
+    if (thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha) {
+        const float dphi = asinf(sa / sc) * 1.002f + 1e-4f;
+        const float pc = atan2f(uy, ux);
+        const float inv_dph = (float)M.n_phi * 0.15915494f;
+        const int jlo = (int)ceilf((pc - dphi) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + dphi) * inv_dph - 0.5f + 1e-3f);
+        if (jhi < jlo) return false;
+        // whole column PAIRS (2k, 2k+1): the pair kernel loads (cos, sin) of both columns with one aligned 64-bit load each
+        const int plo = jlo >> 1, phi_ = jhi >> 1;                  // arithmetic shifts: floor for negative jlo
+        nj = 2 * (phi_ - plo + 1);
+        if (nj < M.n_phi) { j0 = (2 * plo) % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
+    }
+    r = {i0, i1 - i0 + 1, j0, nj};
+    return true;
+}
+
+// One escaping ray's test line -> 0, 1 or 2 rectangles.  Returns false when the ray must go to the tile kernel.
+__device__ __forceinline__ bool line_rects(const MapParams& M, const f3& L, const f3& v, uint32_t& r1, uint32_t& r2) {
+    r1 = 0u; r2 = 0u;
+    if (M.n_theta > RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || (M.n_phi & 1) || M.force_tiles) return false;
+    const float R = M.det_R, W = M.det_W;
+    const float vv = dot3(v, v);
+    if (!(vv > 0.25f)) return false;
+    const float inv = rsqrtf(vv);
+    const f3 vh = {v.x * inv, v.y * inv, v.z * inv};
+    const f3 Lp = {L.x, L.y, L.z + 100.0f};
+    const float t0 = -dot3(Lp, vh);
+    const f3 m = {Lp.x + t0 * vh.x, Lp.y + t0 * vh.y, Lp.z + t0 * vh.z};
+    const float h2 = dot3(m, m), h = sqrtf(h2);
+    const float tp2 = R * R - h2, qmax = 2.0f * h * W + W * W;
+    if (!(tp2 > 1.2f * qmax)) return h > R + W;            // far miss: nothing to test (true); grazing: tile kernel (false)
+    const float tp = sqrtf(tp2);
+    const float amax = tp - sqrtf(tp2 - qmax);
+    const float chord = sqrtf(W * W + amax * amax) * 1.002f;
+    if (!(chord < R)) return false;
+    const float alpha = 2.0f * asinf(chord / (2.0f * R)) + 1e-4f;
+    const float invR = 1.0f / R;
+    LineRect a, b;
+    const bool ha = cap_rect(M, (m.x + tp * vh.x) * invR, (m.y + tp * vh.y) * invR, (m.z + tp * vh.z) * invR, alpha, a);
+    const bool hb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, (m.z - tp * vh.z) * invR, alpha, b);
+    if (ha && hb) {
+        // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
+        const bool rows = a.i0 < b.i0 + b.ni && b.i0 < a.i0 + a.ni;
+        if (rows) return false;
+    }
+    if ((ha ? a.ni * a.nj : 0) + (hb ? b.ni * b.nj : 0) > RECT_MAX_BINS) return false;
+    if (ha) r1 = pack_rect(a);
+    if (hb) { if (ha) r2 = pack_rect(b); else r1 = pack_rect(b); }
+    return true;
+}
+
+// records -> two dense lists of the escaping rays' test lines (L.xyz, v.x | v.yz, rect1, rect2): lines_r for the
+// ray-stationary kernel, lines_t (rectangle words unused) for the tile kernel.  Order is irrelevant (integer counts).
+// TRACEONCE_COMPAT: the line from the origin through the exit point (fluxAtObserverFast.C:1181).
+__global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __restrict__ rec, uint32_t n, const MapParams M,
+                                                       float4* __restrict__ lines_r, float4* __restrict__ lines_t,
+                                                       unsigned int* __restrict__ n_lines /* [0] rect, [1] tile */) {
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool pf = false, rect = false; f3 pos, dir, L = {0.f, 0.f, 0.f}, v = {0.f, 0.f, 0.f}; uint32_t hits, status, r1 = 0u, r2 = 0u;
+        if (i < n) {
+            load_record(rec, i, pos, dir, hits, status);
+            pf = port_flag(M.count_all, M.exit_zf, pos, status);
+        }
+        if (pf) {
+            if (M.mode == ALTB_MAP_TRACEONCE_COMPAT) {
+                const float inv = 1.0f / sqrtf(dot3(pos, pos));
+                L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
+            } else { L = pos; v = dir; }
+            rect = line_rects(M, L, v, r1, r2);
+        }
+        const unsigned mr = __ballot_sync(FULL, pf && rect && r1 != 0u), mt = __ballot_sync(FULL, pf && !rect);
+        unsigned base_r = 0, base_t = 0;
+        if (lane == 0) {
+            if (mr) base_r = atomicAdd(n_lines, (unsigned)__popc(mr));
+            if (mt) base_t = atomicAdd(n_lines + 1, (unsigned)__popc(mt));
+        }
+        base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
+        if (pf && (!rect || r1 != 0u)) {
+            const unsigned below = (1u << lane) - 1u;
+            float4* dst = rect ? lines_r + 2 * (size_t)(base_r + __popc(mr & below)) : lines_t + 2 * (size_t)(base_t + __popc(mt & below));
+            dst[0] = make_float4(L.x, L.y, L.z, v.x);
+            dst[1] = make_float4(v.y, v.z, __uint_as_float(r1), __uint_as_float(r2));
+        }
+    }
+}
+
+// line_hit of two neighbouring phi bins of one theta row, packed: cp = (cos phi_a, cos phi_b), sp likewise; same operations,
+// same order, same bits as line_hit
+__device__ __forceinline__ void line_hit2(const float4 row, const float2 cp, const float2 sp, float w2, const f3& L, const f3& v,
+                                          bool& hit_a, bool& hit_b) {
+    const float rs = row.x, pz = row.y, st = row.z, ct = row.w;
+    const float2 rs2 = make_float2(rs, rs), st2 = make_float2(st, st);
+    const float2 p0 = __fmul2_rn(rs2, cp), p1 = __fmul2_rn(rs2, sp);
+    const float2 t0 = __fmul2_rn(st2, sp), n1 = __fmul2_rn(st2, cp);
+    const float2 n0 = make_float2(-t0.x, -t0.y);
+    const float n2 = -ct;
+    const float vzn = v.z * n2;
+    const float2 dot = __ffma2_rn(make_float2(v.x, v.x), n0, __ffma2_rn(make_float2(v.y, v.y), n1, make_float2(vzn, vzn)));
+    const float2 d0 = __fadd2_rn(make_float2(L.x, L.x), make_float2(-p0.x, -p0.y));
+    const float2 d1 = __fadd2_rn(make_float2(L.y, L.y), make_float2(-p1.x, -p1.y));
+    const float d2 = L.z - pz;
+    const float d2n = d2 * n2;
+    const float2 num = __ffma2_rn(d0, n0, __ffma2_rn(d1, n1, make_float2(d2n, d2n)));
+    const float2 nvx = __fmul2_rn(num, make_float2(v.x, v.x)), nvy = __fmul2_rn(num, make_float2(v.y, v.y)), nvz = __fmul2_rn(num, make_float2(v.z, v.z));
+    const float2 q0 = __ffma2_rn(dot, d0, make_float2(-nvx.x, -nvx.y));
+    const float2 q1 = __ffma2_rn(dot, d1, make_float2(-nvy.x, -nvy.y));
+    const float2 q2 = __ffma2_rn(dot, make_float2(d2, d2), make_float2(-nvz.x, -nvz.y));
+    const float2 r2 = __ffma2_rn(q0, q0, __ffma2_rn(q1, q1, __fmul2_rn(q2, q2)));
+    const float2 lim = __fmul2_rn(make_float2(w2, w2), __fmul2_rn(dot, dot));
+    hit_a = (fabsf(dot.x) >= 1e-10f) && (r2.x <= lim.x);
+    hit_b = (fabsf(dot.y) >= 1e-10f) && (r2.y <= lim.y);
+}
+
+static constexpr int RECT_THREADS = 256;
+// dynamic shared memory: float4 row4[n_theta]; float cp[2 n_phi]; float sp[2 n_phi] (each table twice in a row: a rectangle
+// that wraps around phi = 360 deg reads straight on); uint32 hist[n_bins].  n_phi is even (line_rects).
+__global__ void __launch_bounds__(RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
+                                                                const MapParams M, unsigned long long* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char rect_smem[];
+    const int nb = M.n_theta * M.n_phi, np = M.n_phi;
+    float4* s_row = reinterpret_cast<float4*>(rect_smem);
+    float* s_cp = reinterpret_cast<float*>(s_row + M.n_theta);
+    float* s_sp = s_cp + 2 * np;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(s_sp + 2 * np);
+    for (int i = threadIdx.x; i < M.n_theta; i += RECT_THREADS) s_row[i] = M.row4[i];
+    for (int j = threadIdx.x; j < 2 * np; j += RECT_THREADS) { const float2 c = M.col2[j < np ? j : j - np]; s_cp[j] = c.x; s_sp[j] = c.y; }
+    for (int b = threadIdx.x; b < nb; b += RECT_THREADS) hist[b] = 0u;
+    __syncthreads();
+    const unsigned n_lines = *n_lines_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = (blockIdx.x * RECT_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * RECT_THREADS) >> 5;
+    for (unsigned r = gw; r < n_lines; r += nw) {                 // one ray per warp pass (uniform loads: one transaction each)
+        const float4 ra = __ldg(lines + 2 * (size_t)r), rb = __ldg(lines + 2 * (size_t)r + 1);
+        const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const uint32_t ru = __float_as_uint(k ? rb.w : rb.z);
+            if (!ru) break;
+            const LineRect R = unpack_rect(ru);
+            const int npair = R.nj >> 1, total = R.ni * npair;
+            // lane t of the pass -> (row ii, pair jp); the next pass is 32 pairs further: ii += 32 / npair, jp += 32 % npair (+ carry)
+            const int q32 = 32 / npair, r32 = 32 - q32 * npair;
+            int ii = lane / npair, jp = lane - ii * npair;
+            for (int t = lane; t < total; t += 32) {
+                const int i = R.i0 + ii, jx = R.j0 + 2 * jp;        // jx < 2 n_phi: index into the doubled tables
+                bool ha, hb;
+                line_hit2(s_row[i], *reinterpret_cast<const float2*>(s_cp + jx), *reinterpret_cast<const float2*>(s_sp + jx), M.w2, L, v, ha, hb);
+                if (ha | hb) {
+                    const int j = jx >= np ? jx - np : jx;          // even, j + 1 < n_phi
+                    unsigned int* hp = hist + i * np + j;
+                    if (ha) atomicAdd(hp, 1u);
+                    if (hb) atomicAdd(hp + 1, 1u);
+                }
+                ii += q32; jp += r32;
+                if (jp >= npair) { jp -= npair; ii++; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += RECT_THREADS) {
+        const unsigned int c = hist[b];
+        if (c) atomicAdd(counts + b, (unsigned long long)c);
     }
 }
 
