@@ -112,6 +112,7 @@ def load_library():
     L.altb_destroy.argtypes = [vp]
     L.altb_destroy.restype = None
     L.altb_set_batch.argtypes = [vp, u64]
+    L.altb_collective.argtypes = [vp]
     L.altb_set_contract.argtypes = [vp, C.c_int]
     L.altb_get_contract.argtypes = [vp]
     L.altb_launch_count.argtypes = [vp]
@@ -177,6 +178,11 @@ class Context:
     @property
     def launches(self):
         return int(self._L.altb_launch_count(self._h))
+
+    @property
+    def collective(self):
+        """How a multi-device context merges its maps: "none" (one device), "nccl" or "host"."""
+        return ("none", "nccl", "host")[int(self._L.altb_collective(self._h))]
 
     @property
     def trace_launches(self):

@@ -1,6 +1,9 @@
 // altb_api.cu -- C ABI (include/altair_b200.h) over the sm_100a kernels.  Host-side plumbing only:
 // scene validation, first-event setup, device buffers, launches, multi-device fan-out inside
 // one process.  No CPU fallback: every entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -52,8 +55,40 @@ struct DevCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
+// NCCL through dlopen: a context with several devices merges the per-device maps with ONE all-reduce over NVLink (SURVEY 8b:
+// "ctx owns streams / NCCL comms / device buffers").  Loaded on demand so that single-GPU hosts need no NCCL and a torch
+// process keeps the copy it already loaded (same soname); only the six entry points below are used.
+struct NcclApi {
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+};
+static const NcclApi* nccl_api() {
+    static NcclApi api;
+    static int state = 0;      // 0 not tried, 1 ok, -1 unavailable
+    if (state == 0) {
+        state = -1;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.CommInitAll = (decltype(api.CommInitAll))dlsym(h, "ncclCommInitAll");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            if (api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString) state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+
 struct altb_ctx {
     std::vector<DevCtx> devs;
+    std::vector<ncclComm_t> comms;    // one per device when the context owns several (empty: host merge)
     uint64_t batch = DEFAULT_BATCH;
     int contract = ALTB_CONTRACT_EXACT;
     bool batch_user = false;          // altb_set_batch was called: the direction sink honours it too (default there: 2^31)
@@ -129,6 +164,10 @@ extern "C" int altb_device_count(void) {
 
 extern "C" void altb_destroy(altb_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->comms.empty())
+        if (const NcclApi* N = nccl_api())
+            for (size_t i = 0; i < ctx->comms.size(); i++)
+                if (ctx->comms[i]) { cudaSetDevice(ctx->devs[i].dev); cudaStreamSynchronize(ctx->devs[i].stream); N->CommDestroy(ctx->comms[i]); }
     for (auto& d : ctx->devs) {
         if (d.dev < 0) continue;
         cudaSetDevice(d.dev);
@@ -196,8 +235,29 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
         }
         for (auto& ev : d.ev) cudaEventCreate(&ev);
     }
+    if (n_devices > 1 && !getenv("ALTB_NO_NCCL")) {
+        // the context owns the communicators of its devices; without NCCL on the host the maps are merged on the host instead
+        if (const NcclApi* N = nccl_api()) {
+            std::vector<int> ids(n_devices);
+            for (int i = 0; i < n_devices; i++) ids[i] = ctx->devs[i].dev;
+            ctx->comms.assign(n_devices, nullptr);
+            const ncclResult_t r = N->CommInitAll(ctx->comms.data(), n_devices, ids.data());
+            if (r != ncclSuccess) {
+                const std::string msg = N->GetErrorString(r);
+                ctx->comms.clear();
+                altb_destroy(ctx);
+                return fail(ALTB_E_CUDA, "altb_create: ncclCommInitAll over %d devices failed: %s", n_devices, msg.c_str());
+            }
+        }
+    }
     *out = ctx;
     return 0;
+}
+
+// how a multi-device context merges its per-device maps: 0 = one device (nothing to merge), 1 = NCCL all-reduce, 2 = host sum
+extern "C" int altb_collective(const altb_ctx* ctx) {
+    if (!ctx || ctx->devs.size() < 2) return 0;
+    return ctx->comms.empty() ? 2 : 1;
 }
 
 extern "C" int altb_set_batch(altb_ctx* ctx, uint64_t batch_rays) {
@@ -730,7 +790,8 @@ extern "C" int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n
     const uint64_t nb = (uint64_t)map->n_theta * map->n_phi;
     const int nd = (int)ctx->devs.size();
     const uint64_t words = (uint64_t)n_scenes * (nb + 8);
-    // rays are split evenly over the context's devices; each accumulates its own map, the host adds them
+    // rays are split evenly over the context's devices; each accumulates its own map; the maps are merged by one NCCL
+    // all-reduce (contexts with several devices own communicators) or, without NCCL on the host, summed on the host
     std::vector<std::vector<float>> tms(nd, std::vector<float>(2 * n_scenes, 0.f));
     for (int i = 0; i < nd; i++) {
         DevCtx& d = ctx->devs[i];
@@ -749,11 +810,7 @@ extern "C" int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n
     }
     std::vector<unsigned long long> host(words);
     if (stats) memset(stats, 0, sizeof(altb_stats) * n_scenes);
-    for (int i = 0; i < nd; i++) {
-        DevCtx& d = ctx->devs[i];
-        CK(cudaSetDevice(d.dev));
-        CK(cudaMemcpyAsync(host.data(), d.counts, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaStreamSynchronize(d.stream));
+    auto add_host = [&](int i) {
         for (uint64_t j = 0; j < (uint64_t)n_scenes * nb; j++) counts[j] += host[j];
         if (stats)
             for (int s = 0; s < n_scenes; s++) {
@@ -762,6 +819,31 @@ extern "C" int altb_trace_fluxmap(altb_ctx* ctx, const altb_scene* scenes, int n
                 stats[s].n_absorbed += p[3]; stats[s].n_suspended += p[4]; stats[s].n_bounces += p[5];
                 stats[s].t_trace_s += tms[i][s] * 1e-3; stats[s].t_map_s += tms[i][n_scenes + s] * 1e-3;
             }
+    };
+    if (nd > 1 && !ctx->comms.empty()) {
+        // ONE all-reduce of [counts | stats] (uint64 sums: bit-identical whatever the device count), one copy to the host
+        const NcclApi* N = nccl_api();
+        ncclResult_t r = N->GroupStart();
+        for (int i = 0; i < nd && r == ncclSuccess; i++) {
+            DevCtx& d = ctx->devs[i];
+            r = N->AllReduce(d.counts, d.counts, words, ncclUint64, ncclSum, ctx->comms[i], d.stream);
+        }
+        const ncclResult_t r2 = N->GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) return fail(ALTB_E_CUDA, "altb_trace_fluxmap: ncclAllReduce failed: %s", N->GetErrorString(r));
+        DevCtx& d0 = ctx->devs[0];
+        CK(cudaSetDevice(d0.dev));
+        CK(cudaMemcpyAsync(host.data(), d0.counts, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+        for (int i = 0; i < nd; i++) { CK(cudaSetDevice(ctx->devs[i].dev)); CK(cudaStreamSynchronize(ctx->devs[i].stream)); }
+        add_host(0);
+        return 0;
+    }
+    for (int i = 0; i < nd; i++) {
+        DevCtx& d = ctx->devs[i];
+        CK(cudaSetDevice(d.dev));
+        CK(cudaMemcpyAsync(host.data(), d.counts, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        add_host(i);
     }
     return 0;
 }

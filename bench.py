@@ -287,6 +287,28 @@ def _run_ours(args):
     c_probe, s_probe = tr.step(PROBE_RAYS, ray_id0=0)
     map_crc = "%08x" % (zlib.crc32(np.ascontiguousarray(c_probe).tobytes() + np.ascontiguousarray(s_probe[:, :6]).tobytes()) & 0xffffffff)
 
+    # ---- N > 1: the same probe through ONE process driving all N GPUs -- altb_create(devices, N) owns NCCL communicators and
+    #      merges the per-device maps with one ncclAllReduce inside the C ABI (what the C++ macros use).  Rank 0 does it while
+    #      the other ranks wait at the barrier; its CRC must equal map_crc.
+    inproc = None
+    if world > 1 and not args.no_inproc:
+        barrier()
+        if rank == 0:
+            try:
+                t0 = time.perf_counter()
+                with A.Context(list(range(world))) as many:
+                    many.set_contract(A.CONTRACT_FAST if args.contract == "fast" else A.CONTRACT_EXACT)
+                    t1 = time.perf_counter()
+                    c_in, s_in = many.trace_fluxmap(sc, src, PROBE_RAYS, mp, seed=4357, ray_id0=0)
+                    t2 = time.perf_counter()
+                    s_arr = np.array([[s_in[0][k] for k in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces")]], dtype=np.uint64)
+                    crc_in = "%08x" % (zlib.crc32(np.ascontiguousarray(c_in).tobytes() + s_arr.tobytes()) & 0xffffffff)
+                    inproc = {"devices": world, "collective": many.collective, "map_crc": crc_in, "equals_map_crc": crc_in == map_crc,
+                              "create_s": t1 - t0, "probe_s": t2 - t1}
+            except Exception as e:
+                inproc = {"devices": world, "error": str(e)}
+        barrier()
+
     # ---- per-kernel timing for the roofline (CUDA events inside the library, on its own stream, around the trace launches)
     l0, tl0 = ctx.launches, ctx.trace_launches
     _, kst = ctx.trace_fluxmap(sc, src, total // world, mp, seed=4357, ray_id0=next_id[0] + rank * (total // world))
@@ -321,7 +343,7 @@ def _run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "map_crc": map_crc,
             "map_crc_note": f"CRC-32 of the all-reduced map+stats of ray ids 0..{PROBE_RAYS - 1}; identical at every N",
-            "other_scaling": other, "roofline": roofline, "clocks": clk,
+            "other_scaling": other, "inproc_context": inproc, "roofline": roofline, "clocks": clk,
             "reference_recorded": {"value": REF_RECORDED, "unit": UNIT, "note": "BASELINE.md, author's PC, <=4 threads"}}
     if world == 1 and not args.no_cpu:
         try:
@@ -367,6 +389,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=90.0, help="seconds the reference arm may spend on its K steps")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the secondary scaling measurement")
+    ap.add_argument("--no-inproc", action="store_true", help="N > 1: skip rank 0's in-process multi-device probe (NCCL inside the C ABI)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

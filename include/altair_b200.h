@@ -82,8 +82,13 @@ typedef struct { float pos[3]; float dir[3]; uint32_t n_hits; uint32_t status; }
 
 typedef struct altb_ctx altb_ctx;
 
-/* devices == NULL: use device 0..n_devices-1 (n_devices <= 0: all visible devices). */
+/* devices == NULL: use device 0..n_devices-1 (n_devices <= 0: all visible devices).  A context of several devices is what
+ * SetMaxThreads(k) is to the reference (fluxAtObserverFast.C:1083-1087): the rays of a call are split over the devices by
+ * ray id, and the context owns one NCCL communicator per device (ncclCommInitAll; libnccl.so.2 is loaded on demand) to merge
+ * the per-device maps with ONE all-reduce over NVLink -- uint64 sums, so the result is bit-identical for 1, 2, 4, 8 devices.
+ * Without NCCL on the host (or with ALTB_NO_NCCL=1) the maps are summed on the host instead; altb_collective() tells which. */
 int  altb_create(altb_ctx** out, const int* devices, int n_devices);
+int  altb_collective(const altb_ctx* ctx);     /* 0: one device, 1: NCCL all-reduce, 2: host sum */
 void altb_destroy(altb_ctx* ctx);
 const char* altb_last_error(void);
 int  altb_version(void);

@@ -457,19 +457,34 @@ def test_full_size_properties(ctx, altb):
 
 
 def test_in_process_multi_device_context(altb, ctx):
-    """altb_create(devices, n): one host thread drives several GPUs (what the C++ macros use); rays are split by
-    global id, the host adds the integer maps -> identical to the single-device result."""
+    """altb_create(devices, n): one host thread drives several GPUs (what the C++ macros use: `threads` of the reference's
+    sweepDetector = SetMaxThreads).  Rays are split by global id; the context owns the NCCL communicators and merges the
+    per-device maps with one all-reduce (host sum with ALTB_NO_NCCL=1) -> identical to the single-device result, for the
+    record path (LINE) and for the in-kernel direction sink with batched scenes."""
+    import os
     import torch
+    assert ctx.collective == "none"
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs in one process (covered by the world_size-2 gloo test on CPU)")
+        pytest.skip("needs 2 GPUs in one process (covered by bench.py's rank-0 in-process probe at N > 1 and by the gloo test on CPU)")
     n = 3_000_001
-    gm = altb.map_spec(mode=altb.MAP_LINE)
-    one, st1 = ctx.trace_fluxmap(altb.scene(), altb.source(), n, gm, seed=SEED)
-    with altb.Context(list(range(torch.cuda.device_count()))) as many:
-        cnt, stn = many.trace_fluxmap(altb.scene(), altb.source(), n, gm, seed=SEED)
-    assert np.array_equal(one, cnt)
-    for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
-        assert st1[0][key] == stn[0][key]
+    devs = list(range(torch.cuda.device_count()))
+    scenes = [altb.scene(theta_max=t, brdf_kind=1) for t in (160.0, 170.0)]
+    for mode in (altb.MAP_LINE, altb.MAP_DIRECTION):
+        gm = altb.map_spec(mode=mode)
+        one, st1 = ctx.trace_fluxmap(scenes, altb.source(), n, gm, seed=SEED)
+        for no_nccl in (False, True):
+            if no_nccl:
+                os.environ["ALTB_NO_NCCL"] = "1"
+            try:
+                with altb.Context(devs) as many:
+                    assert many.collective == ("host" if no_nccl else "nccl")
+                    cnt, stn = many.trace_fluxmap(scenes, altb.source(), n, gm, seed=SEED)
+            finally:
+                os.environ.pop("ALTB_NO_NCCL", None)
+            assert np.array_equal(one, cnt)
+            for s in range(2):
+                for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+                    assert st1[s][key] == stn[s][key]
 
 
 def test_map_stage_alone_on_host_records(ctx, oracle, altb):
