@@ -131,7 +131,7 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
 static constexpr int TRACE_THREADS = ALTB_TRACE_THREADS;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 #ifndef ALTB_BOUNCES_PER_CHECK
-#define ALTB_BOUNCES_PER_CHECK 3
+#define ALTB_BOUNCES_PER_CHECK 4
 #endif
 #ifndef ALTB_BPC_UNROLL
 #define ALTB_BPC_UNROLL 1
