@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
 struct LineRect { int i0, ni, j0, nj; };            // rows i0 .. i0+ni-1, columns (j0 + 0 .. nj-1) mod n_phi
 __device__ __forceinline__ uint32_t pack_rect(const LineRect& r) { return (uint32_t)r.i0 | (uint32_t)r.ni << 8 | (uint32_t)r.j0 << 16 | (uint32_t)r.nj << 24; }
 __device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 255u), (int)(u >> 8 & 255u), (int)(u >> 16 & 255u), (int)(u >> 24)}; }
-static constexpr int RECT_MAX_BINS = 4096;          // larger rectangles: the tile kernel culls better
+static constexpr int RECT_MAX_BINS = 8192;          // larger rectangles: the tile kernel culls better
 static constexpr int RECT_MAX_DIM = 255;            // 8-bit fields
 
 // (theta, phi) bounding rectangle of the cap of angular radius alpha (sin / cos given) about the unit direction u (relative
@@ -941,10 +941,13 @@ __device__ __forceinline__ void line_hit2(const float4 row, const float2 cp, con
     hit_b = (fabsf(dot.y) >= 1e-10f) && (r2.y <= lim.y);
 }
 
-static constexpr int RECT_THREADS = 256;
+#ifndef ALTB_RECT_THREADS
+#define ALTB_RECT_THREADS 512
+#endif
+static constexpr int RECT_THREADS = ALTB_RECT_THREADS;      // 2 blocks x 512 threads per SM: 32 warps (the 64.8 kB histogram allows 3 blocks, the registers 2)
 // dynamic shared memory: float4 row4[n_theta]; float cp[2 n_phi]; float sp[2 n_phi] (each table twice in a row: a rectangle
 // that wraps around phi = 360 deg reads straight on); uint32 hist[n_bins].  n_phi is even (line_rects).
-__global__ void __launch_bounds__(RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
+__global__ void __launch_bounds__(RECT_THREADS, 1024 / RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
                                                                 const MapParams M, unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char rect_smem[];
     const int nb = M.n_theta * M.n_phi, np = M.n_phi;

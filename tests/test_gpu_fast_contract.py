@@ -64,11 +64,21 @@ def test_replay_against_double_precision_oracle_fast(fast, oracle, altb, kw):
     ref_bin = np.array([oracle.lib().orc_direction_bin(C.byref(om), r["dir"].ctypes.data_as(C.POINTER(C.c_float)))
                         if p else -1 for r, p in zip(ref, ref_port)], dtype=np.int32)
     bad = (g_rec["status"] != ref["status"]) | (g_port.astype(bool) != ref_port) | (g_bin != ref_bin)
-    assert bad.mean() <= 1e-4, (kw, bad.mean())
+    # The allowance is about FP32 against FP64, not about the contract: on the last scene (every ray leaves, after 134 hits
+    # on average, 40 % of them specular) the EXACT contract is at 1.8e-4 itself (tests/tools/replay_noise.py); there the
+    # fast contract must stay within sampling error of the exact one.
+    fast.set_contract(altb.CONTRACT_EXACT)
+    e_rec, e_bin, e_port = fast.replay(altb.scene(**kw), ray0, tape, off, altb.map_spec(mode=altb.MAP_DIRECTION))
+    fast.set_contract(altb.CONTRACT_FAST)
+    bad_e = (e_rec["status"] != ref["status"]) | (e_port.astype(bool) != ref_port) | (e_bin != ref_bin)
+    allow = max(1e-4, bad_e.mean() + 3 * np.sqrt(max(bad_e.mean(), 1e-6) / n))
+    assert bad.mean() <= allow, (kw, bad.mean(), bad_e.mean())
+    if "reflectance" not in kw:
+        assert bad.mean() <= 1e-4 and bad_e.mean() <= 1e-4, (kw, bad.mean(), bad_e.mean())
     # beyond the north star's criterion: hit counts, and end directions to FP32 noise (an absorbed ray's status and hit
     # count follow from the draws alone, so a trajectory that parted earlier shows up here)
     worse = bad | (g_rec["n_hits"] != ref["n_hits"]) | (np.abs(g_rec["dir"] - ref["dir"]).max(axis=1) > 1e-3)
-    assert worse.mean() <= 3e-4, (kw, worse.mean())
+    assert worse.mean() <= 3 * allow, (kw, worse.mean())
 
 
 @pytest.mark.parametrize("kw", [dict(theta_max=170.0), dict(theta_max=170.0, brdf_kind=1)])
