@@ -490,7 +490,7 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
         M.t_theta = d.map_M.t_theta; M.t_phi = d.map_M.t_phi; M.nt_theta = d.map_M.nt_theta; M.nt_phi = d.map_M.nt_phi;
         M.rs = d.map_M.rs; M.pz = d.map_M.pz; M.st = d.map_M.st; M.ct = d.map_M.ct; M.cp = d.map_M.cp; M.sp = d.map_M.sp;
         M.tiles = d.map_M.tiles; M.supers = d.map_M.supers;
-        M.row4 = d.map_M.row4; M.col2 = d.map_M.col2; M.det_R = d.map_M.det_R; M.det_W = d.map_M.det_W;
+        M.row4 = d.map_M.row4; M.col2 = d.map_M.col2; M.det_R = d.map_M.det_R; M.det_Wr = d.map_M.det_Wr;
         ms.n_tiles = d.map_n_tiles; ms.line_smem = d.map_line_smem; ms.rect_smem = d.map_rect_smem;
         return 0;
     }
@@ -586,8 +586,8 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
     M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
     M.row4 = reinterpret_cast<const float4*>(d.tables + flat); M.col2 = reinterpret_cast<const float2*>(d.tables + flat + 4 * nt);
-    M.det_R = (float)map->det_radius; M.det_W = (float)(hw + 0.5);
-    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)nt * sizeof(float4) + (size_t)4 * np * sizeof(float);
+    M.det_R = (float)map->det_radius; M.det_Wr = (float)(hw + 0.05);      // f32 evaluation of the test moves the rim by < 1e-3 cm
+    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)nt * sizeof(float4) + (size_t)np * sizeof(float4);
     d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_rect_smem = ms.rect_smem; d.map_cached = true;
     return 0;
 }

@@ -517,7 +517,7 @@ struct MapParams {
     int use_smem_hist;
     const double* dir_tab;         // DIRECTION mode: bin edges (direction_bin)
     int force_tiles;               // LINE modes: every ray to the tile kernel (ALTB_LINE_TILES=1, A/B measurements)
-    float det_R, det_W;            // LINE modes: detector-hemisphere radius; det_width / 2 + 0.5 cm of f32 slack (k_prepare_lines)
+    float det_R, det_Wr;           // LINE modes: detector-hemisphere radius; det_width / 2 + 0.05 cm of f32 slack (k_prepare_lines)
     const float4* row4;            // LINE modes: (rs, pz, st, ct) per theta row, packed for one 128-bit load
     const float2* col2;            // LINE modes: (cp, sp) per phi column
     int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
@@ -845,7 +845,7 @@ __device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy,
 __device__ __forceinline__ bool line_rects(const MapParams& M, const f3& L, const f3& v, uint32_t& r1, uint32_t& r2) {
     r1 = 0u; r2 = 0u;
     if (M.n_theta > RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || (M.n_phi & 1) || M.force_tiles) return false;
-    const float R = M.det_R, W = M.det_W;
+    const float R = M.det_R, W = M.det_Wr;
     const float vv = dot3(v, v);
     if (!(vv > 0.25f)) return false;
     const float inv = rsqrtf(vv);
@@ -942,45 +942,53 @@ __device__ __forceinline__ void line_hit2(const float4 row, const float2 cp, con
 }
 
 #ifndef ALTB_RECT_THREADS
-#define ALTB_RECT_THREADS 512
+#define ALTB_RECT_THREADS 1024
 #endif
-static constexpr int RECT_THREADS = ALTB_RECT_THREADS;      // 2 blocks x 512 threads per SM: 32 warps (the 64.8 kB histogram allows 3 blocks, the registers 2)
-// dynamic shared memory: float4 row4[n_theta]; float cp[2 n_phi]; float sp[2 n_phi] (each table twice in a row: a rectangle
-// that wraps around phi = 360 deg reads straight on); uint32 hist[n_bins].  n_phi is even (line_rects).
+static constexpr int RECT_THREADS = ALTB_RECT_THREADS;      // one 1024-thread block per SM: 32 warps (64 registers), ONE histogram to flush
+// dynamic shared memory: float4 row4[n_theta]; float4 colp[n_phi] -- entry k = (cos, cos, sin, sin) of columns 2k', 2k'+1 with
+// k' = k mod (n_phi / 2): the pair table twice in a row, so a rectangle that wraps around phi = 360 deg reads straight on;
+// uint32 hist[n_bins].  n_phi is even (line_rects).
 __global__ void __launch_bounds__(RECT_THREADS, 1024 / RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
                                                                 const MapParams M, unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char rect_smem[];
-    const int nb = M.n_theta * M.n_phi, np = M.n_phi;
+    const int nb = M.n_theta * M.n_phi, np = M.n_phi, nph = M.n_phi >> 1;
     float4* s_row = reinterpret_cast<float4*>(rect_smem);
-    float* s_cp = reinterpret_cast<float*>(s_row + M.n_theta);
-    float* s_sp = s_cp + 2 * np;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(s_sp + 2 * np);
+    float4* s_col = s_row + M.n_theta;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(s_col + np);
     for (int i = threadIdx.x; i < M.n_theta; i += RECT_THREADS) s_row[i] = M.row4[i];
-    for (int j = threadIdx.x; j < 2 * np; j += RECT_THREADS) { const float2 c = M.col2[j < np ? j : j - np]; s_cp[j] = c.x; s_sp[j] = c.y; }
+    for (int k = threadIdx.x; k < np; k += RECT_THREADS) {
+        const int kk = k < nph ? k : k - nph;
+        const float2 a = M.col2[2 * kk], b = M.col2[2 * kk + 1];
+        s_col[k] = make_float4(a.x, b.x, a.y, b.y);
+    }
     for (int b = threadIdx.x; b < nb; b += RECT_THREADS) hist[b] = 0u;
     __syncthreads();
     const unsigned n_lines = *n_lines_ptr;
     const int lane = threadIdx.x & 31;
     const unsigned gw = (blockIdx.x * RECT_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * RECT_THREADS) >> 5;
-    for (unsigned r = gw; r < n_lines; r += nw) {                 // one ray per warp pass (uniform loads: one transaction each)
-        const float4 ra = __ldg(lines + 2 * (size_t)r), rb = __ldg(lines + 2 * (size_t)r + 1);
+    // one ray per warp pass (uniform loads: one transaction each); the next ray's line is in flight while this one is tested
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+    if (gw < n_lines) { ra = __ldg(lines + 2 * (size_t)gw); rb = __ldg(lines + 2 * (size_t)gw + 1); }
+    for (unsigned r = gw; r < n_lines; r += nw) {
         const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
+        const uint32_t rect0 = __float_as_uint(rb.z), rect1 = __float_as_uint(rb.w);
+        if (r + nw < n_lines) { ra = __ldg(lines + 2 * (size_t)(r + nw)); rb = __ldg(lines + 2 * (size_t)(r + nw) + 1); }
 #pragma unroll 1
         for (int k = 0; k < 2; k++) {
-            const uint32_t ru = __float_as_uint(k ? rb.w : rb.z);
+            const uint32_t ru = k ? rect1 : rect0;
             if (!ru) break;
             const LineRect R = unpack_rect(ru);
-            const int npair = R.nj >> 1, total = R.ni * npair;
+            const int npair = R.nj >> 1, total = R.ni * npair, p0 = R.j0 >> 1;
             // lane t of the pass -> (row ii, pair jp); the next pass is 32 pairs further: ii += 32 / npair, jp += 32 % npair (+ carry)
             const int q32 = 32 / npair, r32 = 32 - q32 * npair;
             int ii = lane / npair, jp = lane - ii * npair;
             for (int t = lane; t < total; t += 32) {
-                const int i = R.i0 + ii, jx = R.j0 + 2 * jp;        // jx < 2 n_phi: index into the doubled tables
+                const int i = R.i0 + ii, px = p0 + jp;              // px < n_phi: index into the doubled pair table
+                const float4 c = s_col[px];
                 bool ha, hb;
-                line_hit2(s_row[i], *reinterpret_cast<const float2*>(s_cp + jx), *reinterpret_cast<const float2*>(s_sp + jx), M.w2, L, v, ha, hb);
+                line_hit2(s_row[i], make_float2(c.x, c.y), make_float2(c.z, c.w), M.w2, L, v, ha, hb);
                 if (ha | hb) {
-                    const int j = jx >= np ? jx - np : jx;          // even, j + 1 < n_phi
-                    unsigned int* hp = hist + i * np + j;
+                    unsigned int* hp = hist + i * np + 2 * (px >= nph ? px - nph : px);
                     if (ha) atomicAdd(hp, 1u);
                     if (hb) atomicAdd(hp + 1, 1u);
                 }
