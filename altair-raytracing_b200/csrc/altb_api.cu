@@ -587,7 +587,7 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
     M.row4 = reinterpret_cast<const float4*>(d.tables + flat); M.col2 = reinterpret_cast<const float2*>(d.tables + flat + 4 * nt);
     M.det_R = (float)map->det_radius; M.det_Wr = (float)(hw + 0.05);      // f32 evaluation of the test moves the rim by < 1e-3 cm
-    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)nt * sizeof(float4) + (size_t)np * sizeof(float4);
+    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)(nt + 1) * sizeof(float4) + (size_t)2 * np * sizeof(float2);
     d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_rect_smem = ms.rect_smem; d.map_cached = true;
     return 0;
 }

@@ -805,8 +805,10 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
 // k_prepare_lines computes the rectangle(s) of every escaping ray, one ray per lane; rays whose rectangles would be wasteful
 // (grazing lines of the TRACEONCE_COMPAT semantics, lines that miss the sphere, overlapping caps) go to the tile kernel.
 // k_map_line_rect is ray-stationary: a warp takes one ray at a time and tests the rectangle 64 bins per pass -- each lane
-// two neighbouring phi bins of one row with packed FP32 (FMUL2 / FFMA2 / FADD2: the same IEEE results as line_hit, 30
-// instead of 48 instructions per pair) -- and hits go to a per-block shared-memory histogram with shared atomics.
+// two neighbouring theta rows of one column with packed FP32 (FMUL2 / FFMA2 / FADD2: the same IEEE results as line_hit,
+// 27 instead of 48 instructions per pair; rows are paired rather than columns because a cap spans ~50 rows but only ~10
+// columns: rounding to whole pairs costs 2 % instead of 15 % of the tests) -- and hits go to a per-block shared-memory
+// histogram with shared atomics.
 struct LineRect { int i0, ni, j0, nj; };            // rows i0 .. i0+ni-1, columns (j0 + 0 .. nj-1) mod n_phi
 __device__ __forceinline__ uint32_t pack_rect(const LineRect& r) { return (uint32_t)r.i0 | (uint32_t)r.ni << 8 | (uint32_t)r.j0 << 16 | (uint32_t)r.nj << 24; }
 __device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 255u), (int)(u >> 8 & 255u), (int)(u >> 16 & 255u), (int)(u >> 24)}; }
@@ -824,6 +826,8 @@ __device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy,
     int i0 = (int)ceilf(tlo * inv_dth - 0.5f - 1e-3f), i1 = (int)floorf(thi * inv_dth - 0.5f + 1e-3f);
     i0 = max(i0, 0); i1 = min(i1, M.n_theta - 1);
     if (i1 < i0) return false;
+    // whole row PAIRS (2k, 2k+1): the pair kernel tests two neighbouring theta rows of one column per lane
+    i0 &= ~1; i1 |= 1;
     int j0 = 0, nj = M.n_phi;
     const float sa = sinf(alpha), sc = sinf(thc);
     if (thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha) {
@@ -831,11 +835,9 @@ __device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy,
         const float pc = atan2f(uy, ux);
         const float inv_dph = (float)M.n_phi * 0.15915494f;
         const int jlo = (int)ceilf((pc - dphi) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + dphi) * inv_dph - 0.5f + 1e-3f);
-        if (jhi < jlo) return false;
-        // whole column PAIRS (2k, 2k+1): the pair kernel loads (cos, sin) of both columns with one aligned 64-bit load each
-        const int plo = jlo >> 1, phi_ = jhi >> 1;                  // arithmetic shifts: floor for negative jlo
-        nj = 2 * (phi_ - plo + 1);
-        if (nj < M.n_phi) { j0 = (2 * plo) % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
+        nj = jhi - jlo + 1;
+        if (nj <= 0) return false;
+        if (nj < M.n_phi) { j0 = jlo % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
     }
     r = {i0, i1 - i0 + 1, j0, nj};
     return true;
@@ -844,7 +846,7 @@ __device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy,
 // One escaping ray's test line -> 0, 1 or 2 rectangles.  Returns false when the ray must go to the tile kernel.
 __device__ __forceinline__ bool line_rects(const MapParams& M, const f3& L, const f3& v, uint32_t& r1, uint32_t& r2) {
     r1 = 0u; r2 = 0u;
-    if (M.n_theta > RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || (M.n_phi & 1) || M.force_tiles) return false;
+    if (M.n_theta >= RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || M.force_tiles) return false;
     const float R = M.det_R, W = M.det_Wr;
     const float vv = dot3(v, v);
     if (!(vv > 0.25f)) return false;
@@ -914,27 +916,23 @@ __global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __rest
     }
 }
 
-// line_hit of two neighbouring phi bins of one theta row, packed: cp = (cos phi_a, cos phi_b), sp likewise; same operations,
-// same order, same bits as line_hit
-__device__ __forceinline__ void line_hit2(const float4 row, const float2 cp, const float2 sp, float w2, const f3& L, const f3& v,
-                                          bool& hit_a, bool& hit_b) {
-    const float rs = row.x, pz = row.y, st = row.z, ct = row.w;
-    const float2 rs2 = make_float2(rs, rs), st2 = make_float2(st, st);
-    const float2 p0 = __fmul2_rn(rs2, cp), p1 = __fmul2_rn(rs2, sp);
-    const float2 t0 = __fmul2_rn(st2, sp), n1 = __fmul2_rn(st2, cp);
-    const float2 n0 = make_float2(-t0.x, -t0.y);
-    const float n2 = -ct;
-    const float vzn = v.z * n2;
-    const float2 dot = __ffma2_rn(make_float2(v.x, v.x), n0, __ffma2_rn(make_float2(v.y, v.y), n1, make_float2(vzn, vzn)));
+// line_hit of two neighbouring theta rows (a, b) of one phi column, packed: rs = (rs_a, rs_b) etc.; same operations, same
+// order, same bits as line_hit
+__device__ __forceinline__ void line_hit2(const float2 rs, const float2 pz, const float2 st, const float2 ct, const float cp, const float sp,
+                                          float w2, const f3& L, const f3& v, bool& hit_a, bool& hit_b) {
+    const float2 cp2 = make_float2(cp, cp), sp2 = make_float2(sp, sp);
+    const float2 p0 = __fmul2_rn(rs, cp2), p1 = __fmul2_rn(rs, sp2);
+    const float2 t0 = __fmul2_rn(st, sp2), n1 = __fmul2_rn(st, cp2);
+    const float2 n0 = make_float2(-t0.x, -t0.y), n2 = make_float2(-ct.x, -ct.y);
+    const float2 dot = __ffma2_rn(make_float2(v.x, v.x), n0, __ffma2_rn(make_float2(v.y, v.y), n1, __fmul2_rn(make_float2(v.z, v.z), n2)));
     const float2 d0 = __fadd2_rn(make_float2(L.x, L.x), make_float2(-p0.x, -p0.y));
     const float2 d1 = __fadd2_rn(make_float2(L.y, L.y), make_float2(-p1.x, -p1.y));
-    const float d2 = L.z - pz;
-    const float d2n = d2 * n2;
-    const float2 num = __ffma2_rn(d0, n0, __ffma2_rn(d1, n1, make_float2(d2n, d2n)));
+    const float2 d2 = __fadd2_rn(make_float2(L.z, L.z), make_float2(-pz.x, -pz.y));
+    const float2 num = __ffma2_rn(d0, n0, __ffma2_rn(d1, n1, __fmul2_rn(d2, n2)));
     const float2 nvx = __fmul2_rn(num, make_float2(v.x, v.x)), nvy = __fmul2_rn(num, make_float2(v.y, v.y)), nvz = __fmul2_rn(num, make_float2(v.z, v.z));
     const float2 q0 = __ffma2_rn(dot, d0, make_float2(-nvx.x, -nvx.y));
     const float2 q1 = __ffma2_rn(dot, d1, make_float2(-nvy.x, -nvy.y));
-    const float2 q2 = __ffma2_rn(dot, make_float2(d2, d2), make_float2(-nvz.x, -nvz.y));
+    const float2 q2 = __ffma2_rn(dot, d2, make_float2(-nvz.x, -nvz.y));
     const float2 r2 = __ffma2_rn(q0, q0, __ffma2_rn(q1, q1, __fmul2_rn(q2, q2)));
     const float2 lim = __fmul2_rn(make_float2(w2, w2), __fmul2_rn(dot, dot));
     hit_a = (fabsf(dot.x) >= 1e-10f) && (r2.x <= lim.x);
@@ -945,22 +943,22 @@ __device__ __forceinline__ void line_hit2(const float4 row, const float2 cp, con
 #define ALTB_RECT_THREADS 1024
 #endif
 static constexpr int RECT_THREADS = ALTB_RECT_THREADS;      // one 1024-thread block per SM: 32 warps (64 registers), ONE histogram to flush
-// dynamic shared memory: float4 row4[n_theta]; float4 colp[n_phi] -- entry k = (cos, cos, sin, sin) of columns 2k', 2k'+1 with
-// k' = k mod (n_phi / 2): the pair table twice in a row, so a rectangle that wraps around phi = 360 deg reads straight on;
-// uint32 hist[n_bins].  n_phi is even (line_rects).
+// dynamic shared memory: float4 rowp[2 * ceil(n_theta / 2)] -- entries 2k, 2k+1 = (rs_a, rs_b, pz_a, pz_b), (st_a, st_b, ct_a, ct_b)
+// of the row pair (2k, 2k+1); float2 col[2 n_phi] (cos, sin), the table twice in a row so that a rectangle that wraps around
+// phi = 360 deg reads straight on; uint32 hist[n_bins].
 __global__ void __launch_bounds__(RECT_THREADS, 1024 / RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
                                                                 const MapParams M, unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char rect_smem[];
-    const int nb = M.n_theta * M.n_phi, np = M.n_phi, nph = M.n_phi >> 1;
+    const int nb = M.n_theta * M.n_phi, np = M.n_phi, nrp = (M.n_theta + 1) >> 1;
     float4* s_row = reinterpret_cast<float4*>(rect_smem);
-    float4* s_col = s_row + M.n_theta;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(s_col + np);
-    for (int i = threadIdx.x; i < M.n_theta; i += RECT_THREADS) s_row[i] = M.row4[i];
-    for (int k = threadIdx.x; k < np; k += RECT_THREADS) {
-        const int kk = k < nph ? k : k - nph;
-        const float2 a = M.col2[2 * kk], b = M.col2[2 * kk + 1];
-        s_col[k] = make_float4(a.x, b.x, a.y, b.y);
+    float2* s_col = reinterpret_cast<float2*>(s_row + 2 * nrp);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(s_col + 2 * np);
+    for (int k = threadIdx.x; k < nrp; k += RECT_THREADS) {
+        const float4 a = M.row4[2 * k], b = M.row4[min(2 * k + 1, M.n_theta - 1)];     // (rs, pz, st, ct)
+        s_row[2 * k] = make_float4(a.x, b.x, a.y, b.y);
+        s_row[2 * k + 1] = make_float4(a.z, b.z, a.w, b.w);
     }
+    for (int j = threadIdx.x; j < 2 * np; j += RECT_THREADS) s_col[j] = M.col2[j < np ? j : j - np];
     for (int b = threadIdx.x; b < nb; b += RECT_THREADS) hist[b] = 0u;
     __syncthreads();
     const unsigned n_lines = *n_lines_ptr;
@@ -977,23 +975,26 @@ __global__ void __launch_bounds__(RECT_THREADS, 1024 / RECT_THREADS) k_map_line_
         for (int k = 0; k < 2; k++) {
             const uint32_t ru = k ? rect1 : rect0;
             if (!ru) break;
-            const LineRect R = unpack_rect(ru);
-            const int npair = R.nj >> 1, total = R.ni * npair, p0 = R.j0 >> 1;
-            // lane t of the pass -> (row ii, pair jp); the next pass is 32 pairs further: ii += 32 / npair, jp += 32 % npair (+ carry)
-            const int q32 = 32 / npair, r32 = 32 - q32 * npair;
-            int ii = lane / npair, jp = lane - ii * npair;
+            const LineRect R = unpack_rect(ru);                     // i0 even, ni even
+            const int nj = R.nj, total = (R.ni >> 1) * nj;
+            // lane t of the pass -> (row pair ii, column jj); the next pass is 32 tests further: ii += 32 / nj, jj += 32 % nj (+ carry)
+            const int q32 = 32 / nj, r32 = 32 - q32 * nj;
+            int ii = lane / nj, jj = lane - ii * nj;
             for (int t = lane; t < total; t += 32) {
-                const int i = R.i0 + ii, px = p0 + jp;              // px < n_phi: index into the doubled pair table
-                const float4 c = s_col[px];
+                const int i = R.i0 + 2 * ii, jx = R.j0 + jj;        // jx < 2 n_phi: index into the doubled column table
+                const float4 ra4 = s_row[i], rb4 = s_row[i + 1];
+                const float2 c = s_col[jx];
                 bool ha, hb;
-                line_hit2(s_row[i], make_float2(c.x, c.y), make_float2(c.z, c.w), M.w2, L, v, ha, hb);
+                line_hit2(make_float2(ra4.x, ra4.y), make_float2(ra4.z, ra4.w), make_float2(rb4.x, rb4.y), make_float2(rb4.z, rb4.w),
+                          c.x, c.y, M.w2, L, v, ha, hb);
+                hb = hb && i + 1 < M.n_theta;
                 if (ha | hb) {
-                    unsigned int* hp = hist + i * np + 2 * (px >= nph ? px - nph : px);
+                    unsigned int* hp = hist + i * np + (jx >= np ? jx - np : jx);
                     if (ha) atomicAdd(hp, 1u);
-                    if (hb) atomicAdd(hp + 1, 1u);
+                    if (hb) atomicAdd(hp + np, 1u);
                 }
-                ii += q32; jp += r32;
-                if (jp >= npair) { jp -= npair; ii++; }
+                ii += q32; jj += r32;
+                if (jj >= nj) { jj -= nj; ii++; }
             }
         }
     }
