@@ -869,8 +869,11 @@ __device__ __forceinline__ bool line_rects(const MapParams& M, const f3& L, cons
     const bool hb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, (m.z - tp * vh.z) * invR, alpha, b);
     if (ha && hb) {
         // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
+        // (rays that leave almost sideways: both caps straddle the equator, 180 deg apart in phi -- they share rows, not columns)
         const bool rows = a.i0 < b.i0 + b.ni && b.i0 < a.i0 + a.ni;
-        if (rows) return false;
+        int dab = b.j0 - a.j0; if (dab < 0) dab += M.n_phi;
+        int dba = a.j0 - b.j0; if (dba < 0) dba += M.n_phi;
+        if (rows && (dab < a.nj || dba < b.nj)) return false;
     }
     if ((ha ? a.ni * a.nj : 0) + (hb ? b.ni * b.nj : 0) > RECT_MAX_BINS) return false;
     if (ha) r1 = pack_rect(a);
