@@ -126,6 +126,7 @@ def load_library():
     L.altb_detector_sweep.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, vp, vp, u32, C.c_double, C.c_double,
                                       vp, P(Stats)]
     L.altb_replay.argtypes = [vp, P(Scene), vp, vp, vp, u64, P(MapSpec), vp, vp, vp]
+    L.altb_replay_ex.argtypes = [vp, P(Scene), vp, vp, vp, u64, P(MapSpec), u32, vp, vp, vp]
     L.altb_map_records.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, vp]
     L.altb_map_records_at.argtypes = [vp, P(Scene), P(MapSpec), vp, u64, u64, vp]
     L.altb_probe_f32.argtypes = [vp, C.c_int, vp, u64, vp]
@@ -251,7 +252,7 @@ class Context:
                                                 C.byref(st)))
         return hits, st.as_dict()
 
-    def replay(self, sc, ray0, tape, tape_off, mp=None):
+    def replay(self, sc, ray0, tape, tape_off, mp=None, full_azimuth=False):
         ray0 = np.ascontiguousarray(ray0, dtype=np.float64)
         tape = np.ascontiguousarray(tape, dtype=np.float32)
         tape_off = np.ascontiguousarray(tape_off, dtype=np.uint64)
@@ -259,9 +260,9 @@ class Context:
         rec = np.zeros(n, dtype=RECORD_DTYPE)
         bins = np.full(n, -1, dtype=np.int32)
         port = np.zeros(n, dtype=np.uint8)
-        self._check(self._L.altb_replay(self._h, C.byref(sc), _ptr(ray0), _ptr(tape), _ptr(tape_off), n,
-                                        C.byref(mp) if mp is not None else None, _ptr(rec),
-                                        _ptr(bins) if mp is not None else None, _ptr(port)))
+        self._check(self._L.altb_replay_ex(self._h, C.byref(sc), _ptr(ray0), _ptr(tape), _ptr(tape_off), n,
+                                           C.byref(mp) if mp is not None else None, 1 if full_azimuth else 0, _ptr(rec),
+                                           _ptr(bins) if mp is not None else None, _ptr(port)))
         return rec, bins, port
 
     def map_records(self, sc, mp, rec, ray_id0=0):

@@ -997,15 +997,45 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
 }
 
 // ---------------------------------------------------------------------------------- replay
-template <bool R, int M, int C = CONTRACT_EXACT>
+template <bool R, int M, int C, bool AZ>
 static void launch_replay_t(const ReplayParams& P, const double* ray0, const float4* tape, const unsigned long long* off,
                             const uint32_t* order, altb_record* rec, cudaStream_t st) {
-    k_replay<R, M, C><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, order, rec);
+    k_replay<R, M, C, AZ><<<(P.n + 127) / 128, 128, 0, st>>>(P, ray0, tape, off, order, rec);
+}
+// replay instance = (roughness, model, contract, azimuth precision); the fast contract is built for models 0 and 1
+template <int C, bool AZ>
+static void launch_replay_c(bool rough, int model, const ReplayParams& P, const double* ray0, const float4* tape, const unsigned long long* off,
+                            const uint32_t* order, altb_record* rec, cudaStream_t st) {
+    if (rough) {
+        if (model == 0) return launch_replay_t<true, 0, C, AZ>(P, ray0, tape, off, order, rec, st);
+        if (model == 1) return launch_replay_t<true, 1, C, AZ>(P, ray0, tape, off, order, rec, st);
+        if constexpr (C == CONTRACT_EXACT) {
+            if (model == 2) return launch_replay_t<true, 2, C, AZ>(P, ray0, tape, off, order, rec, st);
+            return launch_replay_t<true, 3, C, AZ>(P, ray0, tape, off, order, rec, st);
+        }
+    } else {
+        if (model == 0) return launch_replay_t<false, 0, C, AZ>(P, ray0, tape, off, order, rec, st);
+        if (model == 1) return launch_replay_t<false, 1, C, AZ>(P, ray0, tape, off, order, rec, st);
+        if constexpr (C == CONTRACT_EXACT) {
+            if (model == 2) return launch_replay_t<false, 2, C, AZ>(P, ray0, tape, off, order, rec, st);
+            return launch_replay_t<false, 3, C, AZ>(P, ray0, tape, off, order, rec, st);
+        }
+    }
 }
 
+extern "C" int altb_replay_ex(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
+                              const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map, uint32_t flags,
+                              altb_record* records, int32_t* bin, uint8_t* port);
 extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
                            const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map,
                            altb_record* records, int32_t* bin, uint8_t* port) {
+    return altb_replay_ex(ctx, scene, ray0, tape, tape_off, n_rays, map, 0u, records, bin, port);
+}
+
+extern "C" int altb_replay_ex(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
+                              const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map, uint32_t flags,
+                              altb_record* records, int32_t* bin, uint8_t* port) {
+    if (flags & ~(uint32_t)ALTB_REPLAY_FULL_AZIMUTH) return fail(ALTB_E_ARG, "altb_replay_ex: unknown flags 0x%x", flags);
     if (!ctx || !scene || !ray0 || !tape_off || (!tape && n_rays && tape_off[n_rays])) return fail(ALTB_E_ARG, "altb_replay: NULL argument");
     if (n_rays == 0) return 0;
     if (n_rays > (1ull << 31)) return fail(ALTB_E_ARG, "altb_replay: at most 2^31 rays per call");
@@ -1052,21 +1082,12 @@ extern "C" int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double*
         }
         const float4* t4 = reinterpret_cast<const float4*>(d_tape);
         cudaEventRecord(d.ev[0], d.stream);
-        if (ctx->contract == ALTB_CONTRACT_FAST && model <= 1) {
-            if (rough) { if (model == 0) launch_replay_t<true, 0, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-                         else launch_replay_t<true, 1, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
-            else       { if (model == 0) launch_replay_t<false, 0, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-                         else launch_replay_t<false, 1, CONTRACT_FAST>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
-        } else if (rough) {
-            if (model == 0) launch_replay_t<true, 0>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else if (model == 1) launch_replay_t<true, 1>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else if (model == 2) launch_replay_t<true, 2>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else launch_replay_t<true, 3>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-        } else {
-            if (model == 0) launch_replay_t<false, 0>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else if (model == 1) launch_replay_t<false, 1>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else if (model == 2) launch_replay_t<false, 2>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
-            else launch_replay_t<false, 3>(P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+        {
+            const bool fast = ctx->contract == ALTB_CONTRACT_FAST && model <= 1, az = (flags & ALTB_REPLAY_FULL_AZIMUTH) != 0;
+            if (fast) { if (az) launch_replay_c<CONTRACT_FAST, true>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+                        else launch_replay_c<CONTRACT_FAST, false>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
+            else      { if (az) launch_replay_c<CONTRACT_EXACT, true>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
+                        else launch_replay_c<CONTRACT_EXACT, false>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
         }
         cudaEventRecord(d.ev[1], d.stream);
         ctx->launches++;

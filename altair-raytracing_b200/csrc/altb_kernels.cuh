@@ -56,18 +56,18 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
     f3 d;
     float dn;
     if (MODEL == 0) {                  // Lambert: composed in the local frame of the true normal, d.nrm falls out
-        if (ROUGH) d = lambert_tilted<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small, dr.u_r, dr.q_phi, dn);
-        else d = lambert_dir<C>(T, nrm, dr.u_r, dr.q_phi, dn);
+        if (ROUGH) d = lambert_tilted<C>(nrm, dr.sc_psi, dr.g0, k.sigma, k.tilt_small, dr.u_r, dr.sc_phi, dn);
+        else d = lambert_dir<C>(nrm, dr.u_r, dr.sc_phi, dn);
     } else {
         f3 n = nrm;
-        if (ROUGH) tilt_normal<C>(T, nrm, dr.q_psi, dr.g0, k.sigma, k.tilt_small, n);
+        if (ROUGH) tilt_normal<C>(nrm, dr.sc_psi, dr.g0, k.sigma, k.tilt_small, n);
         if (MODEL == 2) {
             float m = -2.0f * dot3(s.dir, n);
             d.x = fma_(m, n.x, s.dir.x); d.y = fma_(m, n.y, s.dir.y); d.z = fma_(m, n.z, s.dir.z);
         } else if (MODEL == 3) {
-            d = lobe_dir(T, n, dr.u_r, dr.q_phi, k.lobe_ang);
+            d = lobe_dir(n, dr.u_r, dr.sc_phi, k.lobe_ang);
         } else {
-            d = brdf_mix<C>(T, n, s.dir, dr.spec, dr.u_r, dr.g1, dr.q_phi, k.brdf_s, k.spec_small != 0);
+            d = brdf_mix<C>(n, s.dir, dr.spec, dr.u_r, dr.g1, dr.sc_phi, k.brdf_s, k.spec_small != 0);
         }
         dn = dot3(d, nrm);
     }
@@ -460,7 +460,7 @@ __global__ void k_fill_records(altb_record* rec, uint32_t n, altb_record proto) 
 // ------------------------------------------------------------------------------------ K1r replay
 struct ReplayParams { Geom g; KConsts k; uint32_t n; const float2* sincos; };
 
-template <bool ROUGH, int MODEL, int C>
+template <bool ROUGH, int MODEL, int C, bool FULL_AZ>
 __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayParams P,
                                                 const double* __restrict__ ray0,
                                                 const float4* __restrict__ tape,
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         dr.u_abs = a.x; dr.u_r = a.y; dr.u_phi = a.z; dr.u_sel = a.w;
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
         HitDraws h;
-        hit_from_draws(dr, P.k.rho, P.k.p_spec, h);
+        hit_from_draws<FULL_AZ>(dr, P.k.rho, P.k.p_spec, T, h);
         st = bounce_step<ROUGH, MODEL, false, C>(P.g, P.k, P.k.zc, T, s, h);
     }
     store_record(rec, i, s, st);

@@ -157,6 +157,14 @@ int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const altb_sourc
 int altb_replay(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
                 const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map,
                 altb_record* records, int32_t* bin, uint8_t* port);
+/* The azimuth draws u_phi, u_psi of a tape recorded from this library's own RNG are fixed-point turn fractions (20 and 13
+ * bits) and altb_replay looks their sin / cos up, so such a tape replays bit for bit.  A tape recorded ELSEWHERE (the
+ * reference's own draws, tools/root_dump_tape.C -> tools/tape_from_root_dump.py) carries arbitrary uniforms:
+ * ALTB_REPLAY_FULL_AZIMUTH evaluates sin / cos of 2 pi u at the draw's full float precision instead of truncating it. */
+enum { ALTB_REPLAY_FULL_AZIMUTH = 1 };
+int altb_replay_ex(altb_ctx* ctx, const altb_scene* scene, const double* ray0, const float* tape,
+                   const uint64_t* tape_off, uint64_t n_rays, const altb_map_spec* map, uint32_t flags,
+                   altb_record* records, int32_t* bin, uint8_t* port);
 
 /* Map stage alone on caller-provided records (host). counts is added to.  records[i] is the ray with global id ray_id0 + i:
  * the grouped modes (PER_POSITION, TWOFOLD) derive the detector position from the ray id, so a shard or batch that does not

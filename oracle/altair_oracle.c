@@ -207,9 +207,16 @@ void orc_sincos2pi_q20(uint32_t q, float* s, float* c) {
     *s = fmaf(fmaf(h, a[0], a[1]), B, a[0]);
     *c = fmaf(fmaf(h, a[1], -a[0]), B, a[1]);
 }
-/* tape records carry the fractions as floats */
-static inline void sincos2pi_u13(float u, float* s, float* c) { orc_sincos2pi_q13((uint32_t)(u * 8192.0f), s, c); }
-static inline void sincos2pi_u20(float u, float* s, float* c) { orc_sincos2pi_q20((uint32_t)(u * 1048576.0f) & 0xfffffu, s, c); }
+/* tape records carry the fractions as floats.  g_full_az (orc_replay_ex, ORC_REPLAY_FULL_AZIMUTH): a tape recorded elsewhere
+ * holds arbitrary uniforms -- sin / cos of 2 pi u at full float precision (the polynomial), as altb_replay_ex does; set
+ * before the parallel region, read-only inside. */
+static int g_full_az = 0;
+static inline void sincos2pi_u13(float u, float* s, float* c) {
+    if (g_full_az) orc_sincos2pi_f32(u, s, c); else orc_sincos2pi_q13((uint32_t)(u * 8192.0f), s, c);
+}
+static inline void sincos2pi_u20(float u, float* s, float* c) {
+    if (g_full_az) orc_sincos2pi_f32(u, s, c); else orc_sincos2pi_q20((uint32_t)(u * 1048576.0f) & 0xfffffu, s, c);
+}
 
 /* Contract: |x| <= 0.9 is evaluated directly (quadrant 0 polynomials), anything larger is reduced first. */
 void orc_sincos_f32(float x, float* s, float* c) {
@@ -496,8 +503,14 @@ int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, 
 
 int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
                uint64_t n, int prec, orc_record* rec) {
+    return orc_replay_ex(sc, ray0, tape, tape_off, n, prec, 0u, rec);
+}
+
+int orc_replay_ex(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
+                  uint64_t n, int prec, uint32_t flags, orc_record* rec) {
     geom g; consts_f kf; consts_d kd;
     if (make_geom(sc, &g, &kf, &kd)) return -1;
+    g_full_az = (flags & ORC_REPLAY_FULL_AZIMUTH) != 0;     /* F32 mode only: the F64 mode always takes sin / cos of the full draw */
     int bad = 0;
     #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < (int64_t)n; i++) {
@@ -507,6 +520,7 @@ int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const
         tape_src ts = {tape + 8 * tape_off[i], tape_off[i + 1] - tape_off[i]};
         run_ray(&g, &kf, &kd, prec, kind0, x0, d0, 0, 0, &ts, &rec[i], NULL, NULL, NULL);
     }
+    g_full_az = 0;
     return bad ? -2 : 0;
 }
 

@@ -114,6 +114,11 @@ int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, 
  * tape[8*tape_off[i] .. 8*tape_off[i+1]).  Status ORC_TAPE_END if the tape runs out. */
 int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
                uint64_t n, int prec, orc_record* rec);
+/* ORC_REPLAY_FULL_AZIMUTH: the F32 mode takes sin / cos of 2 pi u_phi, 2 pi u_psi at the draws' full float precision instead
+ * of truncating them to 20 / 13-bit turn fractions (mirror of altb_replay_ex; for tapes not recorded from the Philox path). */
+#define ORC_REPLAY_FULL_AZIMUTH 1u
+int orc_replay_ex(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
+                  uint64_t n, int prec, uint32_t flags, orc_record* rec);
 
 /* Generate the tape a Philox trace of the same rays would use (ORC_F32 trajectory).
  * tape == NULL: only fills tape_off and returns the number of records needed.

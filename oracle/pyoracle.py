@@ -107,6 +107,7 @@ def lib():
     L.orc_trace_f64.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int]
     L.orc_replay.argtypes = [P(Scene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    L.orc_replay_ex.argtypes = [P(Scene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
     L.orc_make_tape.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
                                 C.c_void_p]
     L.orc_make_tape.restype = C.c_int64
@@ -177,13 +178,13 @@ def make_tape(sc, src, n, seed=4357, ray_id0=0):
     return tape[:total], off
 
 
-def replay(sc, ray0, tape, tape_off, prec=F32):
+def replay(sc, ray0, tape, tape_off, prec=F32, full_azimuth=False):
     n = len(tape_off) - 1
     ray0 = np.ascontiguousarray(ray0, dtype=np.float64)
     tape = np.ascontiguousarray(tape, dtype=np.float32)
     tape_off = np.ascontiguousarray(tape_off, dtype=np.uint64)
     rec = np.zeros(n, dtype=RECORD_DTYPE)
-    rc = lib().orc_replay(C.byref(sc), _ptr(ray0), _ptr(tape), _ptr(tape_off), n, prec, _ptr(rec))
+    rc = lib().orc_replay_ex(C.byref(sc), _ptr(ray0), _ptr(tape), _ptr(tape_off), n, prec, 1 if full_azimuth else 0, _ptr(rec))
     if rc:
         raise RuntimeError(f"orc_replay rc={rc}")
     return rec
