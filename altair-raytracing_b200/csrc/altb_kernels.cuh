@@ -19,6 +19,12 @@
 namespace altb {
 
 static constexpr unsigned FULL = 0xffffffffu;
+// fire-and-forget 64-bit add by ONE chosen thread (spelled in PTX: for atomicAdd under `if (lane == 0)` nvcc emits its
+// generic warp-aggregation sequence -- vote, find-leader, popc, multiply -- about ten instructions around each RED)
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 struct RayState {
     f3 pos, dir;
@@ -270,13 +276,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         reinterpret_cast<float4*>(trace_smem)[i] = __ldg(reinterpret_cast<const float4*>(P.sincos) + i);
     __syncthreads();
     const DrawTabs T = make_tabs(trace_smem);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    QEntry* xq = s_q + (size_t)warp * XQCAP;                                       // crossings waiting for the slow path
-    QEntry* rq = P.rq + ((size_t)blockIdx.x * TRACE_WARPS + warp) * RQCAP;         // rays to resume (global memory, rare)
+    // Lane / warp indices, the lane mask and the queue addresses are RE-DERIVED where they are used (special registers, a
+    // shift, an address computation) instead of being held across the loop: at 64 registers per thread every warp-uniform
+    // value kept alive is a spill in the regeneration code (ptxas had pushed the queue pointers, `end` and the exhausted flag
+    // to local memory: 8 LDL / STL per pass).
+#define ALTB_LANE (threadIdx.x & 31u)
+#define ALTB_LTMASK lanemask_lt()
+#define ALTB_XQ (s_q + (size_t)(threadIdx.x >> 5) * XQCAP)                                               /* crossings waiting for the slow path */
+#define ALTB_RQ (P.rq + ((size_t)blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5)) * RQCAP)                 /* rays to resume (global memory, rare) */
     uint32_t nx = 0, nr = 0;          // warp-uniform queue fills
     uint32_t next = 0, end = 0;       // warp-uniform: lane indices [next,end) (slot bits included) are claimed by this warp
-    bool exhausted = false;           // warp-uniform: the global pool is empty
+    // (the global pool is empty  <=>  next > end: no separate flag)
+#define ALTB_EXHAUSTED (next > end)
     bool alive = false;
     uint32_t idx = 0;
     float zc = P.k.zc;                // BATCHED: port plane of this lane's ray
@@ -299,10 +310,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                 if (!BATCHED) {
                     const uint32_t tot = __reduce_add_sync(FULL, hraw & 0x7fffffffu);
                     const uint32_t nsus = __popc(__ballot_sync(FULL, (hraw >> 31) != 0u));
-                    if (lane == 0 && tot) {             // (no shared-memory accumulator + flush at the end: any code after
+                    if (ALTB_LANE == 0 && tot) {             // (no shared-memory accumulator + flush at the end: any code after
                         unsigned long long* gs = trace_stats(P, 1u, 0u);    //  the loop made ptxas spill inside the bounce bodies)
-                        atomicAdd(gs + 4, (unsigned long long)tot);
-                        if (nsus) atomicAdd(gs + 3, (unsigned long long)nsus);
+                        red_add_u64(gs + 4, (unsigned long long)tot);
+                        if (nsus) red_add_u64(gs + 3, (unsigned long long)nsus);
                     }
                 } else if (hraw) {
                     unsigned long long* gs = trace_stats(P, P.n_slots, idx >> shift);
@@ -312,8 +323,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                 if (!alive) s.hits = 0;
             }
             if (nr) {                                   // resume parked rays first
-                const uint32_t rank = __popc(need & lt_mask);
+                const uint32_t rank = __popc(need & ALTB_LTMASK);
                 if (!alive && rank < nr) {
+                    const QEntry* rq = ALTB_RQ;
                     const float4 ea = __ldcg(&rq[nr - 1 - rank].a), eb = __ldcg(&rq[nr - 1 - rank].b);
                     s.pos = {ea.x, ea.y, ea.z}; s.dir = {ea.w, eb.x, eb.y};
                     idx = __float_as_uint(eb.z);
@@ -325,12 +337,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                 __syncwarp();
                 need = __ballot_sync(FULL, !alive);
             }
-            if (need && !exhausted) {
+            if (need && !ALTB_EXHAUSTED) {
                 if (next >= end) {
                     uint32_t q = 0;
-                    if (lane == 0) q = atomicAdd(counter, 1u);
+                    if (ALTB_LANE == 0) q = atomicAdd(counter, 1u);
                     q = __shfl_sync(FULL, q, 0);
-                    if (q >= P.n_chunks) { exhausted = true; next = end = 0; }
+                    if (q >= P.n_chunks) { next = 1; end = 0; }
                     else {
                         uint32_t slot = 0;
                         if (BATCHED) { slot = q / P.cps; q -= slot * P.cps; }
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     }
                 }
                 if (!alive) {
-                    const uint32_t id = next + __popc(need & lt_mask);
+                    const uint32_t id = next + __popc(need & ALTB_LTMASK);
                     if (id < end) {
                         alive = true; idx = id;
                         if (BATCHED) zc = P.slots[id >> shift].zcf;
@@ -347,11 +359,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                         s.hits = 0;
                     }
                 }
-                next = min(end, next + (uint32_t)__popc(need));
+                if (!ALTB_EXHAUSTED) next = min(end, next + (uint32_t)__popc(need));
             }
         }
         const bool any_alive = __any_sync(FULL, alive);
-        if (!any_alive && exhausted && nx == 0 && nr == 0) break;
+        if (!any_alive && ALTB_EXHAUSTED && nx == 0 && nr == 0) break;
 
         // ---- ALTB_BOUNCES_PER_CHECK surface hits per live lane between two regeneration checks
         bool crossing = false;
@@ -384,7 +396,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                     QEntry e;
                     e.a = make_float4(s.pos.x, s.pos.y, s.pos.z, s.dir.x);
                     e.b = make_float4(s.dir.y, s.dir.z, __uint_as_float(idx), __uint_as_float(s.hits));
-                    xq[nx + __popc(cm & lt_mask)] = e;
+                    ALTB_XQ[nx + __popc(cm & ALTB_LTMASK)] = e;
                     if (SINK == SINK_DIRECTION) s.hits = 0;        // the hit count travels with the queue entry
                 }
                 nx += __popc(cm);
@@ -392,14 +404,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
             }
         }
         // ---- drain the crossing queue at full width (or whatever is left once nothing else can run)
-        if (nx >= 32 || (nx && !any_alive && exhausted && nr == 0)) {
+        if (nx >= 32 || (nx && !any_alive && ALTB_EXHAUSTED && nr == 0)) {
             const uint32_t take = min(nx, 32u);
             nx -= take;
-            nr = drain_crossings<ROUGH, MODEL, SINK_, C>(P, T, rec, xq + nx, rq, take, nr);
+            nr = drain_crossings<ROUGH, MODEL, SINK_, C>(P, T, rec, ALTB_XQ + nx, ALTB_RQ, take, nr);
         }
     }
 
 }
+
+#undef ALTB_LANE
+#undef ALTB_LTMASK
+#undef ALTB_XQ
+#undef ALTB_RQ
+#undef ALTB_EXHAUSTED
 
 // SINK_DIRECTION: the blocks' private statistics -> the scenes' 8 statistics words
 // (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces, 0, 0), added to.  One thread per slot.
