@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ray_bounces_per_s_fluxmap"
 UNIT = "ray-bounces/s"
 FLOP_PER_BOUNCE = 100.0          # SURVEY.md 8(d)'s per-unit figure (Lambert + Gaussian roughness): the contract's unit of work
-FLOP_PER_BOUNCE_MODEL = 117.0    # the CustomMirror step actually benched, counted from csrc/altb_math.cuh
+FLOP_PER_BOUNCE_MODEL = 175.0    # what the CustomMirror step executes (FMA = 2), from the per-function ncu table in profiles/ 
 REF_RECORDED = 3.7e6             # reference's own recorded rate, author's PC, <=4 threads
 C3_RAYS = 1_000_000_000          # BASELINE.json configs[2]
 PROBE_RAYS = 10_000_000          # map_crc probe
@@ -177,11 +177,12 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
-def profile_reference():
+def profile_reference(contract):
     """ncu-derived numbers are NOT measured by this run: they are read from the committed capture summary
-    (profiles/*_k_trace_ncu.json, written by tools/ncu_summary.py --json) together with the capture's own configuration."""
+    (profiles/rNN_k_trace_ncu_<contract>.json, written by tools/ncu_summary.py --json) together with the capture's own
+    configuration."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_trace_ncu.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_k_trace_ncu_{contract}.json")))
     if not files:
         return None
     try:
@@ -327,7 +328,7 @@ def _run_ours(args):
                 "avg_launch_ms": kst["t_trace_s"] * 1e3 / n_trace, "map_ms_per_launch": kst["t_map_s"] * 1e3 / n_trace,
                 "bounces_per_s_kernel": kst["n_bounces"] / kst["t_trace_s"],
                 "hbm_bytes_per_bounce_algorithmic": 0.0}
-    prof = profile_reference()
+    prof = profile_reference(args.contract)
     if prof:
         roofline["traffic"] = prof.get("dram_bytes_per_launch")
         roofline["profile_reference"] = prof

@@ -61,6 +61,24 @@ def text(fn, ln):
     return s[ln - 1].strip()[:90] if 0 < ln <= len(s) else ""
 for fn, (e, t) in sorted(per_file.items(), key=lambda x: -x[1][0]):
     print(f"  {e / tot * 100:5.1f}%  thr {t / max(e, 1):4.1f}  {fn}")
+# per function: every source line belongs to the last function header above it (inlined code keeps its own line info)
+def func_of(fn, ln):
+    if fn not in srcs:
+        text(fn, 1)
+    best = "?"
+    for i, l in enumerate(srcs.get(fn, [])[:ln], 1):
+        m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__|__host__|ALTB_HD)[^;{]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", l)
+        if m and not l.strip().startswith("//"):
+            best = m.group(1)
+    return best
+per_func = defaultdict(lambda: [0, 0])
+for (fn, ln), (e, t) in per_line.items():
+    per_func[(fn, func_of(fn, ln))][0] += e; per_func[(fn, func_of(fn, ln))][1] += t
+unit = float(os.environ.get("NCU_BY_LINE_UNITS", "0"))          # e.g. bounces / 32: prints instructions per unit as well
+print("by function:")
+for (fn, f), (e, t) in sorted(per_func.items(), key=lambda x: -x[1][0])[:40]:
+    extra = f"  {e / unit:7.2f} per unit" if unit else ""
+    print(f"  {e / tot * 100:5.2f}%  thr {t / max(e, 1):4.1f}{extra}  {fn}:{f}")
 print("top lines:")
 for (fn, ln), (e, t) in sorted(per_line.items(), key=lambda x: -x[1][0])[:top]:
     print(f"  {e / tot * 100:5.2f}%  thr {t / max(e, 1):4.1f}  {fn}:{ln}  {text(fn, ln)}")
