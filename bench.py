@@ -330,7 +330,11 @@ def _run_ours(args):
                 "hbm_bytes_per_bounce_algorithmic": 0.0}
     prof = profile_reference(args.contract)
     if prof:
-        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+        # the capture's DRAM bytes, scaled from the capture's launch size to this run's launch size (per launch, like `achieved`)
+        if prof.get("dram_bytes_per_launch") and prof.get("bounces_in_launch"):
+            roofline["traffic"] = prof["dram_bytes_per_launch"] * (kst["n_bounces"] / n_trace) / prof["bounces_in_launch"]
+            roofline["traffic_note"] = ("dram__bytes_read+write of the committed ncu capture, scaled by bounces per launch; algorithmic "
+                                        "HBM bytes of the in-kernel direction sink: the 129.7 kB map + statistics per launch")
         roofline["profile_reference"] = prof
     barrier()
     if rank != 0:

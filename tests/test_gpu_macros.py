@@ -181,7 +181,7 @@ def test_full_size_sweepDetector_against_reference_map(M, altb):
           f"hits {int(k.sum())} vs reference {int(k_ref.sum())}")
     assert 0.8 < chi2 < 1.3, chi2
     assert np.abs(zz).max() < 6.0
-    assert abs(k.sum() / k_ref.sum() - 1) < 0.025
+    assert abs(k.sum() / k_ref.sum() - 1) < 0.012          # known systematic: -0.44 % (profiles/r02_residual.json)
     assert "# Number of rays per position: 50000" in text and f"out of {16200 * 50000}" in text
     assert wall < 120
     json.dump({"wall_s": wall, "chi2_ndf": chi2, "max_abs_z": float(np.abs(zz).max()), "hits": int(k.sum()), "hits_reference": int(k_ref.sum()),
@@ -220,7 +220,7 @@ def test_full_size_statistical_parity_other_goldens(M, ctx, altb):
     zz = (k - k_ref)[ok] / np.sqrt(2 * n * p[ok] * (1 - p[ok]))
     out["perposition_163"] = {"chi2_ndf": float((zz ** 2).mean()), "max_abs_z": float(np.abs(zz).max()), "hits": int(k.sum()),
                               "hits_reference": int(k_ref.sum())}
-    assert 0.8 < out["perposition_163"]["chi2_ndf"] < 1.3 and np.abs(zz).max() < 6.0 and abs(k.sum() / k_ref.sum() - 1) < 0.025
+    assert 0.8 < out["perposition_163"]["chi2_ndf"] < 1.3 and np.abs(zz).max() < 6.0 and abs(k.sum() / k_ref.sum() - 1) < 0.012    # known: -0.92 %
     # --- trace-once maps as shipped + escape fractions
     for theta in (160, 164, 170):
         zt = np.load(os.path.join(G, f"traceonce_{theta}.npz"))
@@ -234,7 +234,35 @@ def test_full_size_statistical_parity_other_goldens(M, ctx, altb):
         esc_ref, esc_sig = ref.mean() / 1e5, ref.std(ddof=1) / 1e5 / np.sqrt(ref.size)
         out[f"theta_{theta}"] = {"traceonce_sum_ratio": float(ratio), "escape_fraction": esc, "escape_fraction_reference": esc_ref,
                                  "reference_sigma": esc_sig, "z": (esc - esc_ref) / esc_sig}
-        assert abs(ratio - 1) < 0.02
-        assert abs(esc - esc_ref) < 4 * esc_sig and abs(esc / esc_ref - 1) < 4e-3
+        assert abs(ratio - 1) < 0.015
+        assert abs(esc - esc_ref) < 3 * esc_sig              # 3 sigma of the mean of the reference's own runs (5 or 10 of 1e5 rays)
     print(json.dumps(out))
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "statistical_parity.json"), "w"), indent=1)
+
+
+def test_residual_table_against_reference_maps(ctx, altb):
+    """Tracks the one KNOWN systematic difference between the parity model and the reference: with
+    2e9-ray LINE maps the reference's two complete per-position maps sit up to +-1.7 % off the model per 10-degree band of
+    detector theta, 9-24 sigma of the reference's own Poisson error -- far below its per-bin resolution (every per-bin test
+    passes) but systematic.  Nothing in this environment can resolve it (ROBAST internals); the table is written every round
+    (-> profiles/rNN_residual.json) and the test fails if the residual GROWS beyond its known envelope."""
+    import json
+    G = os.path.join(ROOT, "tests", "golden")
+    n = 2_000_000_000
+    out = {"rays": n, "bands_deg": [[10 * b, 10 * b + 10] for b in range(9)], "note": "reference / model - 1 per band; sigma = reference Poisson"}
+    for name, th in (("perposition_170_dir5_0_0", 170.0), ("perposition_163_dir5_0_0", 163.0)):
+        k_ref = np.load(os.path.join(G, name + ".npz"))["hits"].astype(float).reshape(180, 90)
+        c, st = ctx.trace_fluxmap(altb.scene(theta_max=th), altb.source(), n, altb.map_spec(mode=altb.MAP_LINE), seed=11)
+        exp = 50000.0 * c[0].reshape(180, 90).astype(float) / n
+        ratios, sig = [], []
+        for b in range(9):
+            r, e = k_ref[20 * b:20 * b + 20].sum(), exp[20 * b:20 * b + 20].sum()
+            ratios.append(r / e - 1); sig.append((r - e) / np.sqrt(e))
+        tot = k_ref.sum() / exp.sum() - 1
+        chi2 = float((((k_ref - exp) ** 2 / np.maximum(exp, 1e-9))[exp > 15]).mean())
+        out[f"theta_max_{int(th)}"] = {"ratio_minus_1": [float(x) for x in ratios], "sigma": [float(x) for x in sig], "total_ratio_minus_1": float(tot),
+                                      "chi2_ndf_per_bin": chi2, "escape_fraction": st[0]["n_exit_port"] / n}
+        assert max(abs(x) for x in ratios[:7]) < 0.025, ratios          # known envelope: -1.3 % ... +1.7 %
+        assert abs(tot) < 0.012 and 0.9 < chi2 < 1.15, (tot, chi2)
+    print(json.dumps(out))
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "residual.json"), "w"), indent=1)

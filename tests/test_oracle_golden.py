@@ -72,7 +72,7 @@ def test_traceonce_compat_matches_published_maps(oracle, theta):
     # theta profile (phi-summed rows) agrees within 5 % wherever it is well populated
     row, row_ref = k.reshape(180, 90).sum(1) / n, k_ref.reshape(180, 90).sum(1) / n_ref
     big = row_ref > 0.1 * row_ref.max()
-    assert np.abs(row[big] / row_ref[big] - 1).max() < 0.08
+    assert np.abs(row[big] / row_ref[big] - 1).max() < 0.08      # 3e5 CPU rays: ~3 % statistical per row + the 2-3 % mid-theta residual of SURVEY 8a-6 B
 
 
 def test_exit_direction_distribution_matches_raylog(oracle):
