@@ -359,6 +359,7 @@ static cudaError_t launch_trace_sc(bool rough, int model, const TraceParams& P, 
 }
 template <int C>
 static cudaError_t launch_trace_c(int sink, bool rough, int model, const TraceParams& P, altb_record* rec, unsigned int* counter, int blocks, cudaStream_t st) {
+    if (sink == SINK_LINES) return launch_trace_sc<SINK_LINES, C>(rough, model, P, rec, counter, blocks, st);
     if (sink != SINK_DIRECTION) return launch_trace_sc<SINK_RECORDS, C>(rough, model, P, rec, counter, blocks, st);
     if (P.n_slots > 1) return launch_trace_sc<SINK_DIRECTION_BATCHED, C>(rough, model, P, rec, counter, blocks, st);
     return launch_trace_sc<SINK_DIRECTION, C>(rough, model, P, rec, counter, blocks, st);
@@ -397,6 +398,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     P.shift = 32 - sbits; P.imask = (1u << P.shift) - 1u;
     if ((uint64_t)n >= (1ull << P.shift)) return fail(ALTB_E_ARG, "run_trace: %u rays x %u slots do not fit one launch", n, P.n_slots);
     if (P.n_slots > 1 && sink != SINK_DIRECTION) return fail(ALTB_E_ARG, "run_trace: batched scenes need the direction sink");
+    if (sink == SINK_LINES && P.kind0 != EV_WALL) return fail(ALTB_E_ARG, "run_trace: the lines sink needs a source whose first event is the wall");
     const uint64_t total = (uint64_t)n * P.n_slots;
     int blocks = d.sm_count;                           // persistent: one 1024-thread block per SM
     const uint64_t warps_needed = (total + 31) / 32;
@@ -409,7 +411,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     P.cps = (n + chunk - 1) / chunk;
     P.n_chunks = P.cps * P.n_slots;
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-    if (sink == SINK_DIRECTION) CK(cudaMemsetAsync(gstat, 0, (size_t)blocks * P.n_slots * STAT_WORDS * sizeof(unsigned long long), st));
+    if (sink != SINK_RECORDS) CK(cudaMemsetAsync(gstat, 0, (size_t)blocks * P.n_slots * STAT_WORDS * sizeof(unsigned long long), st));
     cudaError_t le = cudaSuccess;
     if (P.kind0 != EV_WALL) {   // source aimed at the port rim: generic tracer (k_trace's fresh rays start on the sphere)
         if (sink != SINK_RECORDS || P.n_slots != 1) return fail(ALTB_E_ARG, "run_trace: rim-aimed sources go through the record path");
@@ -425,7 +427,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     ctx->launches++;
     ctx->trace_launches++;
     CK(le);
-    if (sink == SINK_DIRECTION) {
+    if (sink != SINK_RECORDS) {
         k_reduce_trace_stats<<<(P.n_slots + 63) / 64, 64, 0, st>>>(P, blocks);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -592,6 +594,34 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
     return 0;
 }
 
+// the two LINE-map kernels on the line buffer (rectangle list from the front, tile list from the back; n_lines[0] / [1])
+static int run_line_kernels(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const MapParams& Mp, const float4* lines, uint32_t lines_cap,
+                            const unsigned int* n_lines, uint32_t n_hint, unsigned long long* d_counts, cudaStream_t st) {
+    if (!Mp.force_tiles) {
+        if (ms.rect_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_map_line_rect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line_rect, RECT_THREADS, ms.rect_smem));
+        if (per_sm < 1) per_sm = 1;
+        int blocks = d.sm_count * per_sm;
+        const int need = (int)((n_hint + 8 * (RECT_THREADS / 32) - 1) / (8 * (RECT_THREADS / 32)));     // >= 8 rays per warp, or fewer blocks
+        if (blocks > need) blocks = std::max(need, 1);
+        k_map_line_rect<<<blocks, RECT_THREADS, ms.rect_smem, st>>>(lines, n_lines, Mp, d_counts);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 1;    // persistent blocks: exactly the resident count (registers, shared memory, threads)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line, LINE_THREADS, ms.line_smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = d.sm_count * per_sm;
+    const int need = (int)((n_hint + LINE_BATCH - 1) / LINE_BATCH);
+    if (blocks > need) blocks = need;
+    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(lines + 2 * (size_t)lines_cap, n_lines + 1, Mp, d_counts);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // records d.rec[0..n) -> counts (+stats)
 static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const altb_record* rec, unsigned int* counter, uint32_t n, uint64_t ray_base,
                    unsigned long long* d_counts, unsigned long long* d_stats, int* d_bin, cudaStream_t st) {
@@ -627,45 +657,21 @@ static int run_map(altb_ctx* ctx, DevCtx& d, const MapSetup& ms, const altb_reco
         CK(cudaGetLastError());
         return 0;
     }
-    // ---- LINE / TRACEONCE_COMPAT: escaping rays -> test lines (+ candidate rectangles) -> ray-stationary kernel, the rest by tiles
-    CK(cudaFuncSetAttribute(k_map_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    if (int rc = ensure(d.lines, d.lines_cap, 4 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;      // two lists of 2 float4 per ray
-    float4* lines_r = d.lines;
-    float4* lines_t = d.lines + 2 * (size_t)std::max<uint64_t>(d.rec_cap, n);
+    // ---- LINE / TRACEONCE_COMPAT on records: escaping rays -> test lines (+ candidate rectangles) -> the two map kernels
+    if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, n))) return rc;      // 2 float4 per ray, both lists
+    const uint32_t lines_cap = (uint32_t)std::min<uint64_t>(d.lines_cap / 2, 0xffffffffull);
     MapParams Mp = M;
-    const bool rect_ok = ms.rect_smem <= 200 * 1024;
-    Mp.force_tiles = !rect_ok || getenv("ALTB_LINE_TILES") != nullptr;
-    CK(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));
+    Mp.force_tiles = ms.rect_smem > 200 * 1024 || getenv("ALTB_LINE_TILES") != nullptr;
+    CK(cudaMemsetAsync(counter + 2, 0, 2 * sizeof(unsigned int), st));
     {
         int cb = d.sm_count * 8;
         const int need = (int)((n + 255) / 256);
         if (cb > need) cb = need;
-        k_prepare_lines<<<cb, 256, 0, st>>>(rec, n, Mp, lines_r, lines_t, counter);
+        k_prepare_lines<<<cb, 256, 0, st>>>(rec, n, Mp, d.lines, lines_cap, counter + 2);
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    if (!Mp.force_tiles) {
-        if (ms.rect_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_map_line_rect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line_rect, RECT_THREADS, ms.rect_smem));
-        if (per_sm < 1) per_sm = 1;
-        int blocks = d.sm_count * per_sm;
-        const int need = (int)((n + 8 * (RECT_THREADS / 32) - 1) / (8 * (RECT_THREADS / 32)));     // >= 8 rays per warp, or fewer blocks
-        if (blocks > need) blocks = std::max(need, 1);
-        k_map_line_rect<<<blocks, RECT_THREADS, ms.rect_smem, st>>>(lines_r, counter, Mp, d_counts);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    int per_sm = 1;    // persistent blocks: exactly the resident count (registers, shared memory, threads)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_line, LINE_THREADS, ms.line_smem));
-    if (per_sm < 1) per_sm = 1;
-    int blocks = d.sm_count * per_sm;
-    const int need = (int)((n + LINE_BATCH - 1) / LINE_BATCH);
-    if (blocks > need) blocks = need;
-    k_map_line<<<blocks, LINE_THREADS, ms.line_smem, st>>>(lines_t, counter + 1, Mp, d_counts);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
+    return run_line_kernels(ctx, d, ms, Mp, d.lines, lines_cap, counter + 2, n, d_counts, st);
 }
 
 // ---------------------------------------------------------------------------------- hot path
@@ -693,6 +699,8 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
     // ---- plan: which scenes share launches
     const bool dir_mode = map->map_mode == ALTB_MAP_DIRECTION;
     auto dir_sink_ok = [&](int s) { return dir_mode && !tss[s].P.g.count_all && (tss[s].P.kind0 == EV_WALL || tss[s].P.kind0 == EV_EXIT); };
+    const bool line_mode = map->map_mode == ALTB_MAP_LINE || map->map_mode == ALTB_MAP_TRACEONCE_COMPAT;
+    auto lines_sink_ok = [&](int s) { return line_mode && !tss[s].P.g.count_all && tss[s].P.kind0 == EV_WALL && !getenv("ALTB_LINE_RECORDS"); };
     std::vector<std::vector<int>> groups;
     std::vector<char> seen((size_t)n_scenes, 0);
     for (int s = 0; s < n_scenes; s++) {
@@ -717,7 +725,7 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
         const bool dsink = dir_sink_ok(g[0]);
         const uint64_t cap = dsink ? dir_cap(g.size()) : batch_rec;
         n_launches += (n_rays + cap - 1) / cap;
-        any_rec |= !dsink;
+        any_rec |= !dsink && !lines_sink_ok(g[0]);
     }
     if (any_rec) if (int rc = ensure(d.rec, d.rec_cap, batch_rec)) return rc;
     const bool overlap = !t_trace_ms && dir_mode && n_launches >= 2 && !getenv("ALTB_NO_OVERLAP");
@@ -732,8 +740,17 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
     for (size_t gi = 0; gi < groups.size() && !rc_all; gi++) {
         const std::vector<int>& g = groups[gi];
         TraceSetup& ts = tss[g[0]];
-        const bool dsink = dir_sink_ok(g[0]);
+        const bool dsink = dir_sink_ok(g[0]), lsink = lines_sink_ok(g[0]);
         float tt = 0.f, tm = 0.f;
+        MapParams Ml = ms.M;
+        if (lsink) {
+            ts.P.slots[0].scene = (uint32_t)g[0];
+            ts.P.stats_base = d_stats; ts.P.counts_base = d_counts; ts.P.nb = (uint32_t)nb; ts.P.n_theta = map->n_theta; ts.P.n_phi = map->n_phi;
+            Ml.force_tiles = ms.rect_smem > 200 * 1024 || getenv("ALTB_LINE_TILES") != nullptr;
+            ts.P.rp = {map->n_theta, map->n_phi, Ml.force_tiles, map->map_mode == ALTB_MAP_TRACEONCE_COMPAT, Ml.det_R, Ml.det_Wr};
+            if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, batch_rec))) return rc;
+            ts.P.lines = d.lines; ts.P.lines_cap = (uint32_t)std::min<uint64_t>(d.lines_cap / 2, 0xffffffffull);
+        }
         if (dsink) {
             ts.P.n_slots = (uint32_t)g.size();
             for (size_t j = 0; j < g.size(); j++) { ts.P.slots[j] = tss[g[j]].P.slots[0]; ts.P.slots[j].scene = (uint32_t)g[j]; }
@@ -747,9 +764,12 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
             const uint32_t n = (uint32_t)piece_len(ray_id0 + off, n_rays - off, cap);
             const LaunchSlot& L = ls[overlap ? (launch_no & 1) : 0];
             if (t_trace_ms) CK(cudaEventRecord(d.ev[0], L.st));
-            rc_all = run_trace(ctx, d, ts, dsink ? SINK_DIRECTION : SINK_RECORDS, ray_id0 + off, n, L.rec, L.counter, L.rq, L.gstat, L.st);
+            if (lsink) { ts.P.n_lines = L.counter + 2; CK(cudaMemsetAsync(L.counter + 2, 0, 2 * sizeof(unsigned int), L.st)); }
+            rc_all = run_trace(ctx, d, ts, dsink ? SINK_DIRECTION : (lsink ? SINK_LINES : SINK_RECORDS), ray_id0 + off, n, L.rec, L.counter, L.rq, L.gstat, L.st);
             if (!rc_all && t_trace_ms) CK(cudaEventRecord(d.ev[1], L.st));
-            if (!rc_all && !dsink)
+            if (!rc_all && lsink)
+                rc_all = run_line_kernels(ctx, d, ms, Ml, d.lines, ts.P.lines_cap, L.counter + 2, n, d_counts + (size_t)g[0] * nb, L.st);
+            else if (!rc_all && !dsink)
                 rc_all = run_map(ctx, d, msg, L.rec, L.counter, n, ray_id0 + off, d_counts + (size_t)g[0] * nb, d_stats + (size_t)g[0] * 8, nullptr, L.st);
             if (!rc_all && t_trace_ms) {
                 CK(cudaEventRecord(d.ev[2], L.st));

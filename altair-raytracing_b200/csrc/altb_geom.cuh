@@ -40,6 +40,9 @@ static constexpr int MAX_SLOTS = 192;
 
 struct QEntry { float4 a, b; };        // a parked ray: pos.xyz, dir.x | dir.yz, idx, hits
 
+// what the candidate-rectangle computation of the LINE maps needs (altb_kernels.cuh: line_rects)
+struct RectParams { int n_theta, n_phi, force_tiles, compat; float det_R, det_Wr; };
+
 struct TraceParams {
     Geom g;               // slot-dependent fields (zc, T2, cth, sth) are those of slot 0; the slow path patches them per ray
     KConsts k;
@@ -60,6 +63,9 @@ struct TraceParams {
     unsigned long long* counts_base; unsigned long long* stats_base;
     uint32_t nb; int n_theta, n_phi;
     const double* dir_tab;   // bin edges of the direction map (altb_kernels.cuh: direction_bin)
+    // SINK_LINES: the escaping rays' test lines go straight to the LINE-map stage -- rectangle list from the front of `lines`,
+    // tile list from its back (2 float4 per ray, lines_cap rays in all); n_lines[0] / [1] count them
+    RectParams rp; float4* lines; unsigned int* n_lines; uint32_t lines_cap;
     const float2* sincos; // device tables: SC_N sin/cos entries + LG_N log entries (altb_math.cuh: DrawTabs)
     SceneSlot slots[MAX_SLOTS];
 };

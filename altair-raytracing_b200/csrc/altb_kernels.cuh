@@ -106,6 +106,81 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ candidate rectangles of the LINE maps
+// (used by k_trace's LINES sink and by k_prepare_lines; the geometry is explained above k_prepare_lines)
+struct LineRect { int i0, ni, j0, nj; };            // rows i0 .. i0+ni-1, columns (j0 + 0 .. nj-1) mod n_phi
+__device__ __forceinline__ uint32_t pack_rect(const LineRect& r) { return (uint32_t)r.i0 | (uint32_t)r.ni << 8 | (uint32_t)r.j0 << 16 | (uint32_t)r.nj << 24; }
+__device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 255u), (int)(u >> 8 & 255u), (int)(u >> 16 & 255u), (int)(u >> 24)}; }
+static constexpr int RECT_MAX_BINS = 8192;          // larger rectangles: the tile kernel culls better
+static constexpr int RECT_MAX_DIM = 255;            // 8-bit fields
+
+// (theta, phi) bounding rectangle of the cap of angular radius alpha (sin / cos given) about the unit direction u (relative
+// to c0, z up): false if no bin centre of the lower hemisphere can lie in it
+__device__ __forceinline__ bool cap_rect(const RectParams& M, float ux, float uy, float uz, float alpha, LineRect& r) {
+    const float HALF_PI = 1.5707964f;
+    const float thc = acosf(fminf(fmaxf(-uz, -1.0f), 1.0f));
+    const float tlo = thc - alpha, thi = thc + alpha;
+    if (tlo >= HALF_PI) return false;
+    const float inv_dth = (float)M.n_theta * (1.0f / HALF_PI);
+    int i0 = (int)ceilf(tlo * inv_dth - 0.5f - 1e-3f), i1 = (int)floorf(thi * inv_dth - 0.5f + 1e-3f);
+    i0 = max(i0, 0); i1 = min(i1, M.n_theta - 1);
+    if (i1 < i0) return false;
+    // whole row PAIRS (2k, 2k+1): the pair kernel tests two neighbouring theta rows of one column per lane
+    i0 &= ~1; i1 |= 1;
+    int j0 = 0, nj = M.n_phi;
+    const float sa = sinf(alpha), sc = sinf(thc);
+    if (thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha) {
+        const float dphi = asinf(sa / sc) * 1.002f + 1e-4f;
+        const float pc = atan2f(uy, ux);
+        const float inv_dph = (float)M.n_phi * 0.15915494f;
+        const int jlo = (int)ceilf((pc - dphi) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + dphi) * inv_dph - 0.5f + 1e-3f);
+        nj = jhi - jlo + 1;
+        if (nj <= 0) return false;
+        if (nj < M.n_phi) { j0 = jlo % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
+    }
+    r = {i0, i1 - i0 + 1, j0, nj};
+    return true;
+}
+
+// One escaping ray's test line -> 0, 1 or 2 rectangles.  Returns false when the ray must go to the tile kernel.
+__device__ __forceinline__ bool line_rects(const RectParams& M, const f3& L, const f3& v, uint32_t& r1, uint32_t& r2) {
+    r1 = 0u; r2 = 0u;
+    if (M.n_theta >= RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || M.force_tiles) return false;
+    const float R = M.det_R, W = M.det_Wr;
+    const float vv = dot3(v, v);
+    if (!(vv > 0.25f)) return false;
+    const float inv = rsqrtf(vv);
+    const f3 vh = {v.x * inv, v.y * inv, v.z * inv};
+    const f3 Lp = {L.x, L.y, L.z + 100.0f};
+    const float t0 = -dot3(Lp, vh);
+    const f3 m = {Lp.x + t0 * vh.x, Lp.y + t0 * vh.y, Lp.z + t0 * vh.z};
+    const float h2 = dot3(m, m), h = sqrtf(h2);
+    const float tp2 = R * R - h2, qmax = 2.0f * h * W + W * W;
+    if (!(tp2 > 1.2f * qmax)) return h > R + W;            // far miss: nothing to test (true); grazing: tile kernel (false)
+    const float tp = sqrtf(tp2);
+    const float amax = tp - sqrtf(tp2 - qmax);
+    const float chord = sqrtf(W * W + amax * amax) * 1.002f;
+    if (!(chord < R)) return false;
+    const float alpha = 2.0f * asinf(chord / (2.0f * R)) + 1e-4f;
+    const float invR = 1.0f / R;
+    LineRect a, b;
+    const bool ha = cap_rect(M, (m.x + tp * vh.x) * invR, (m.y + tp * vh.y) * invR, (m.z + tp * vh.z) * invR, alpha, a);
+    const bool hb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, (m.z - tp * vh.z) * invR, alpha, b);
+    if (ha && hb) {
+        // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
+        // (rays that leave almost sideways: both caps straddle the equator, 180 deg apart in phi -- they share rows, not columns)
+        const bool rows = a.i0 < b.i0 + b.ni && b.i0 < a.i0 + a.ni;
+        int dab = b.j0 - a.j0; if (dab < 0) dab += M.n_phi;
+        int dba = a.j0 - b.j0; if (dba < 0) dba += M.n_phi;
+        if (rows && (dab < a.nj || dba < b.nj)) return false;
+    }
+    if ((ha ? a.ni * a.nj : 0) + (hb ? b.ni * b.nj : 0) > RECT_MAX_BINS) return false;
+    if (ha) r1 = pack_rect(a);
+    if (hb) { if (ha) r2 = pack_rect(b); else r1 = pack_rect(b); }
+    return true;
+}
+
+
 // ------------------------------------------------------------------------------------ K1
 // Persistent warps.  Every lane owns one live ray; a lane whose ray ends takes the next ray at once
 // (first from the warp's resume queue, then from ids claimed in chunks off one global counter), so the
@@ -125,6 +200,9 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
 //
 // SINK: where a finished ray goes.
 //   SINK_RECORDS    the 32-byte record rec[slot * n + i] (LINE maps, per-ray results, detector sweeps);
+//   SINK_LINES      LINE-type maps (count_all_status == 0): statistics as in SINK_DIRECTION; the escaping ray's test line and
+//                   its candidate rectangle(s) are computed in the slow path and appended to the lists the map kernels read
+//                   -- no record buffer, no pass over 32 B x all rays to find the 43 % that escaped;
 //   SINK_DIRECTION  nowhere: the escaping ray is binned by exit direction right in the slow path (one global
 //                   RED.64 per escaping ray into its scene's map) and the statistics are kept in per-block
 //                   shared-memory counters (shared atomics at the ray's end, one flush per block): no record round trip,
@@ -146,7 +224,7 @@ static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 // 32 crossings and the drain leaves fewer than 32 behind: nx <= 31 + 32.  Resumed rays are taken back before fresh ids
 // and every crossing frees a lane, so the resume queue holds at most the crossing backlog plus one pass: nr <= 63 + 32.
 static constexpr int XQCAP = 64, RQCAP = 96;
-enum { SINK_RECORDS = 0, SINK_DIRECTION = 1, SINK_DIRECTION_BATCHED = 2 };   // BATCHED: several slots (per-lane port plane)
+enum { SINK_RECORDS = 0, SINK_DIRECTION = 1, SINK_DIRECTION_BATCHED = 2, SINK_LINES = 3 };   // BATCHED: several slots (per-lane port plane)
 // per-slot statistics words of a block (SINK_DIRECTION): exited, through the port, absorbed, suspended, bounces.
 // They live in GLOBAL memory, private to the block (P.gstat[block][slot][STAT_WORDS], zeroed before the launch, summed into
 // the scenes' statistics by k_reduce_trace_stats after it): a finished ray costs two RED.64 (no return value, nothing
@@ -211,12 +289,28 @@ __device__ __noinline__ int edge_bounces(const TraceParams& P, const Geom& g, co
 template <bool ROUGH, int MODEL, int SINK_, int C>
 __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const DrawTabs& T, altb_record* __restrict__ rec,
                                                  const QEntry* q, QEntry* rq, uint32_t take, uint32_t nr) {
-    constexpr bool BATCHED = SINK_ == SINK_DIRECTION_BATCHED;
+    constexpr bool BATCHED = SINK_ == SINK_DIRECTION_BATCHED, LINES = SINK_ == SINK_LINES;
     constexpr int SINK = SINK_ == SINK_RECORDS ? SINK_RECORDS : SINK_DIRECTION;
     const uint32_t shift = BATCHED ? P.shift : 31u, imask = BATCHED ? P.imask : 0x7fffffffu;
     const unsigned lane = threadIdx.x & 31u;
     bool resume = false;
     QEntry e;
+    // LINES: an escaping ray that passes the port test leaves its test line here (0: nothing, 1: rectangle list, 2: tile list)
+    int line_kind = 0; f3 lL = {0.f, 0.f, 0.f}, lv = {0.f, 0.f, 0.f}; uint32_t lr1 = 0u, lr2 = 0u;
+    auto exit_line = [&](float px, float py, float pz, float dx, float dy, float dz, uint32_t hits) {
+        unsigned long long* gs = trace_stats(P, 1u, 0u);
+        stat_end(gs, 0, hits);
+        if (pz < P.k.exit_zf) {
+            atomicAdd(gs + 1, 1ull);
+            if (P.rp.compat) {            // the line from the origin through the exit point (fluxAtObserverFast.C:1181)
+                const f3 pos = {px, py, pz};
+                const float inv = 1.0f / sqrtf(dot3(pos, pos));
+                lL = {0.f, 0.f, 0.f}; lv = {px * inv, py * inv, pz * inv};
+            } else { lL = {px, py, pz}; lv = {dx, dy, dz}; }
+            const bool rect = line_rects(P.rp, lL, lv, lr1, lr2);
+            line_kind = rect ? (lr1 ? 1 : 0) : 2;
+        }
+    };
     if (lane < take) {
         e = q[lane];
         const uint32_t id = __float_as_uint(e.b.z);
@@ -233,7 +327,8 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
                 float4* p = reinterpret_cast<float4*>(rec + id);
                 p[0] = e.a;
                 p[1] = make_float4(e.b.x, e.b.y, e.b.w, __uint_as_float((uint32_t)ALTB_EXITED));
-            } else exit_to_map(P, slot, e.a.z, e.a.w, e.b.x, e.b.y, __float_as_uint(e.b.w));
+            } else if (LINES) exit_line(e.a.x, e.a.y, e.a.z, e.a.w, e.b.x, e.b.y, __float_as_uint(e.b.w));
+            else exit_to_map(P, slot, e.a.z, e.a.w, e.b.x, e.b.y, __float_as_uint(e.b.w));
         } else {
             // Port-edge hit (4 % of the crossings, 3e-4 of the surface hits): bounce on the edge right here, with the
             // generic step, until the ray is back on the inner sphere (resume) or ends.  Few lanes, rare.
@@ -241,7 +336,8 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
             t.pos = {e.a.x, e.a.y, e.a.z}; t.dir = {e.a.w, e.b.x, e.b.y};
             t.hits = __float_as_uint(e.b.w); t.where = EV_EDGE;
             const int st = edge_bounces<ROUGH, MODEL, C>(P, g, T, P.ctr_lo0 + (id & imask), t);
-            if (st == ALTB_EXITED && SINK == SINK_DIRECTION) exit_to_map(P, slot, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
+            if (st == ALTB_EXITED && LINES) exit_line(t.pos.x, t.pos.y, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
+            else if (st == ALTB_EXITED && SINK == SINK_DIRECTION) exit_to_map(P, slot, t.pos.z, t.dir.x, t.dir.y, t.dir.z, t.hits);
             else if (st) {
                 if (SINK == SINK_RECORDS) store_record(rec, id, t, st);
                 else if (st == ALTB_ABSORBED) atomicAdd(trace_stats(P, P.n_slots, slot) + 4, (unsigned long long)t.hits);
@@ -250,6 +346,25 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
                 resume = true;
                 e.a = make_float4(t.pos.x, t.pos.y, t.pos.z, t.dir.x);
                 e.b = make_float4(t.dir.y, t.dir.z, e.b.z, __uint_as_float(t.hits));
+            }
+        }
+    }
+    if (LINES) {                                        // append the test lines: one reservation per list and warp
+        const unsigned mr = __ballot_sync(FULL, line_kind == 1), mt = __ballot_sync(FULL, line_kind == 2);
+        if (mr | mt) {
+            unsigned base_r = 0, base_t = 0;
+            if (lane == 0) {
+                if (mr) base_r = atomicAdd(P.n_lines, (unsigned)__popc(mr));
+                if (mt) base_t = atomicAdd(P.n_lines + 1, (unsigned)__popc(mt));
+            }
+            base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
+            if (line_kind) {
+                const unsigned below = (1u << lane) - 1u;
+                // rectangle list from the front, tile list from the back of the same buffer
+                float4* dst = line_kind == 1 ? P.lines + 2 * (size_t)(base_r + __popc(mr & below))
+                                             : P.lines + 2 * ((size_t)P.lines_cap - 1 - (base_t + __popc(mt & below)));
+                dst[0] = make_float4(lL.x, lL.y, lL.z, lv.x);
+                dst[1] = make_float4(lv.y, lv.z, __uint_as_float(lr1), __uint_as_float(lr2));
             }
         }
     }
@@ -711,7 +826,8 @@ static constexpr int SUPER = 4;             // a super-tile is SUPER x SUPER til
 // dynamic shared memory layout:
 //   float4 rays[LINE_BATCH][2]; uint32 bitmap[n_tiles][LINE_WORDS]; float4 tiles[n_tiles]; float4 supers[n_super];
 //   uint32 sup_ij[n_super]; tables
-__global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restrict__ lines,
+// (its list grows from the BACK of the line buffer: entry e = lines_end[-2 (e + 1)], lines_end[-2 (e + 1) + 1])
+__global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restrict__ lines_end,
                                                            const unsigned int* __restrict__ n_lines_ptr, const MapParams M,
                                                            unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -744,7 +860,7 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
         const int nwords = (nr + 31) >> 5;
         __syncthreads();                                 // previous pass is done with rays / bitmap
         for (int w = tid; w < n_tiles * LINE_WORDS; w += LINE_THREADS) bitmap[w] = 0u;
-        for (int k = tid; k < 2 * nr; k += LINE_THREADS) rays[k] = __ldg(lines + 2 * cur + k);
+        for (int k = tid; k < 2 * nr; k += LINE_THREADS) rays[k] = __ldg(lines_end - 2 * (ptrdiff_t)(cur + (k >> 1) + 1) + (k & 1));
         __syncthreads();
         // ---- phase 1: conservative two-level culling, one ray per warp pass, lanes = (super-)tiles.
         //      dist(centre, line)^2 <= (w + r + slack)^2 is necessary for any bin of the (super-)tile to be hit.
@@ -827,84 +943,13 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
 // 27 instead of 48 instructions per pair; rows are paired rather than columns because a cap spans ~50 rows but only ~10
 // columns: rounding to whole pairs costs 2 % instead of 15 % of the tests) -- and hits go to a per-block shared-memory
 // histogram with shared atomics.
-struct LineRect { int i0, ni, j0, nj; };            // rows i0 .. i0+ni-1, columns (j0 + 0 .. nj-1) mod n_phi
-__device__ __forceinline__ uint32_t pack_rect(const LineRect& r) { return (uint32_t)r.i0 | (uint32_t)r.ni << 8 | (uint32_t)r.j0 << 16 | (uint32_t)r.nj << 24; }
-__device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 255u), (int)(u >> 8 & 255u), (int)(u >> 16 & 255u), (int)(u >> 24)}; }
-static constexpr int RECT_MAX_BINS = 8192;          // larger rectangles: the tile kernel culls better
-static constexpr int RECT_MAX_DIM = 255;            // 8-bit fields
-
-// (theta, phi) bounding rectangle of the cap of angular radius alpha (sin / cos given) about the unit direction u (relative
-// to c0, z up): false if no bin centre of the lower hemisphere can lie in it
-__device__ __forceinline__ bool cap_rect(const MapParams& M, float ux, float uy, float uz, float alpha, LineRect& r) {
-    const float HALF_PI = 1.5707964f;
-    const float thc = acosf(fminf(fmaxf(-uz, -1.0f), 1.0f));
-    const float tlo = thc - alpha, thi = thc + alpha;
-    if (tlo >= HALF_PI) return false;
-    const float inv_dth = (float)M.n_theta * (1.0f / HALF_PI);
-    int i0 = (int)ceilf(tlo * inv_dth - 0.5f - 1e-3f), i1 = (int)floorf(thi * inv_dth - 0.5f + 1e-3f);
-    i0 = max(i0, 0); i1 = min(i1, M.n_theta - 1);
-    if (i1 < i0) return false;
-    // whole row PAIRS (2k, 2k+1): the pair kernel tests two neighbouring theta rows of one column per lane
-    i0 &= ~1; i1 |= 1;
-    int j0 = 0, nj = M.n_phi;
-    const float sa = sinf(alpha), sc = sinf(thc);
-    if (thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha) {
-        const float dphi = asinf(sa / sc) * 1.002f + 1e-4f;
-        const float pc = atan2f(uy, ux);
-        const float inv_dph = (float)M.n_phi * 0.15915494f;
-        const int jlo = (int)ceilf((pc - dphi) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + dphi) * inv_dph - 0.5f + 1e-3f);
-        nj = jhi - jlo + 1;
-        if (nj <= 0) return false;
-        if (nj < M.n_phi) { j0 = jlo % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
-    }
-    r = {i0, i1 - i0 + 1, j0, nj};
-    return true;
-}
-
-// One escaping ray's test line -> 0, 1 or 2 rectangles.  Returns false when the ray must go to the tile kernel.
-__device__ __forceinline__ bool line_rects(const MapParams& M, const f3& L, const f3& v, uint32_t& r1, uint32_t& r2) {
-    r1 = 0u; r2 = 0u;
-    if (M.n_theta >= RECT_MAX_DIM || M.n_phi > RECT_MAX_DIM || M.force_tiles) return false;
-    const float R = M.det_R, W = M.det_Wr;
-    const float vv = dot3(v, v);
-    if (!(vv > 0.25f)) return false;
-    const float inv = rsqrtf(vv);
-    const f3 vh = {v.x * inv, v.y * inv, v.z * inv};
-    const f3 Lp = {L.x, L.y, L.z + 100.0f};
-    const float t0 = -dot3(Lp, vh);
-    const f3 m = {Lp.x + t0 * vh.x, Lp.y + t0 * vh.y, Lp.z + t0 * vh.z};
-    const float h2 = dot3(m, m), h = sqrtf(h2);
-    const float tp2 = R * R - h2, qmax = 2.0f * h * W + W * W;
-    if (!(tp2 > 1.2f * qmax)) return h > R + W;            // far miss: nothing to test (true); grazing: tile kernel (false)
-    const float tp = sqrtf(tp2);
-    const float amax = tp - sqrtf(tp2 - qmax);
-    const float chord = sqrtf(W * W + amax * amax) * 1.002f;
-    if (!(chord < R)) return false;
-    const float alpha = 2.0f * asinf(chord / (2.0f * R)) + 1e-4f;
-    const float invR = 1.0f / R;
-    LineRect a, b;
-    const bool ha = cap_rect(M, (m.x + tp * vh.x) * invR, (m.y + tp * vh.y) * invR, (m.z + tp * vh.z) * invR, alpha, a);
-    const bool hb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, (m.z - tp * vh.z) * invR, alpha, b);
-    if (ha && hb) {
-        // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
-        // (rays that leave almost sideways: both caps straddle the equator, 180 deg apart in phi -- they share rows, not columns)
-        const bool rows = a.i0 < b.i0 + b.ni && b.i0 < a.i0 + a.ni;
-        int dab = b.j0 - a.j0; if (dab < 0) dab += M.n_phi;
-        int dba = a.j0 - b.j0; if (dba < 0) dba += M.n_phi;
-        if (rows && (dab < a.nj || dba < b.nj)) return false;
-    }
-    if ((ha ? a.ni * a.nj : 0) + (hb ? b.ni * b.nj : 0) > RECT_MAX_BINS) return false;
-    if (ha) r1 = pack_rect(a);
-    if (hb) { if (ha) r2 = pack_rect(b); else r1 = pack_rect(b); }
-    return true;
-}
-
-// records -> two dense lists of the escaping rays' test lines (L.xyz, v.x | v.yz, rect1, rect2): lines_r for the
-// ray-stationary kernel, lines_t (rectangle words unused) for the tile kernel.  Order is irrelevant (integer counts).
+// records -> two dense lists of the escaping rays' test lines (L.xyz, v.x | v.yz, rect1, rect2) in ONE buffer: from the front
+// for the ray-stationary kernel, from the back (rectangle words unused) for the tile kernel.  Order is irrelevant (integer counts).
 // TRACEONCE_COMPAT: the line from the origin through the exit point (fluxAtObserverFast.C:1181).
 __global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __restrict__ rec, uint32_t n, const MapParams M,
-                                                       float4* __restrict__ lines_r, float4* __restrict__ lines_t,
+                                                       float4* __restrict__ lines, uint32_t lines_cap,
                                                        unsigned int* __restrict__ n_lines /* [0] rect, [1] tile */) {
+    const RectParams RP = {M.n_theta, M.n_phi, M.force_tiles, M.mode == ALTB_MAP_TRACEONCE_COMPAT, M.det_R, M.det_Wr};
     const unsigned lane = threadIdx.x & 31u;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
@@ -919,7 +964,7 @@ __global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __rest
                 const float inv = 1.0f / sqrtf(dot3(pos, pos));
                 L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
             } else { L = pos; v = dir; }
-            rect = line_rects(M, L, v, r1, r2);
+            rect = line_rects(RP, L, v, r1, r2);
         }
         const unsigned mr = __ballot_sync(FULL, pf && rect && r1 != 0u), mt = __ballot_sync(FULL, pf && !rect);
         unsigned base_r = 0, base_t = 0;
@@ -930,7 +975,8 @@ __global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __rest
         base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
         if (pf && (!rect || r1 != 0u)) {
             const unsigned below = (1u << lane) - 1u;
-            float4* dst = rect ? lines_r + 2 * (size_t)(base_r + __popc(mr & below)) : lines_t + 2 * (size_t)(base_t + __popc(mt & below));
+            float4* dst = rect ? lines + 2 * (size_t)(base_r + __popc(mr & below))          // rectangle list from the front,
+                               : lines + 2 * ((size_t)lines_cap - 1 - (base_t + __popc(mt & below)));   // tile list from the back
             dst[0] = make_float4(L.x, L.y, L.z, v.x);
             dst[1] = make_float4(v.y, v.z, __uint_as_float(r1), __uint_as_float(r2));
         }

@@ -329,13 +329,15 @@ def _run_ours(args):
                 "bounces_per_s_kernel": kst["n_bounces"] / kst["t_trace_s"],
                 "hbm_bytes_per_bounce_algorithmic": 0.0}
     prof = profile_reference(args.contract)
-    if prof:
+    if prof and args.map == "direction":
         # the capture's DRAM bytes, scaled from the capture's launch size to this run's launch size (per launch, like `achieved`)
         if prof.get("dram_bytes_per_launch") and prof.get("bounces_in_launch"):
             roofline["traffic"] = prof["dram_bytes_per_launch"] * (kst["n_bounces"] / n_trace) / prof["bounces_in_launch"]
             roofline["traffic_note"] = ("dram__bytes_read+write of the committed ncu capture, scaled by bounces per launch; algorithmic "
                                         "HBM bytes of the in-kernel direction sink: the 129.7 kB map + statistics per launch")
         roofline["profile_reference"] = prof
+    elif prof:
+        roofline["profile_reference_note"] = "the committed k_trace capture is of the direction-map instance; not attached to a LINE-map run"
     barrier()
     if rank != 0:
         if world > 1:
