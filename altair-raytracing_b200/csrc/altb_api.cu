@@ -37,7 +37,8 @@ struct DevCtx {
     unsigned long long* stats = nullptr;      // [8]
     float* tables = nullptr; uint64_t tables_cap = 0;   // floats
     float4* tiles = nullptr; uint64_t tiles_cap = 0;
-    float4* lines = nullptr; uint64_t lines_cap = 0;    // dense list of escaping rays for the line maps (2 float4 each)
+    float4* lines = nullptr; uint64_t lines_cap = 0;    // escaping rays' test lines for the line maps (2 float4 each): rectangle list from the front, tile list from the back
+    float4* raw = nullptr; uint64_t raw_cap = 0;        // LINES sink of k_trace: escaping rays' end points and directions (2 float4 each)
     float2* sincos = nullptr;                           // SC_N-entry azimuth table (altb_math.cuh: SinCosTab)
     // second record buffer + counter + two worker streams: consecutive launches of a DIRECTION-mode job alternate between
     // them, so that the tail of one persistent launch (its last long rays) overlaps the start of the next one
@@ -172,7 +173,7 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
         if (d.dev < 0) continue;
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.sincos);
+        cudaFree(d.rec); cudaFree(d.counter); cudaFree(d.counts); cudaFree(d.stats); cudaFree(d.tables); cudaFree(d.tiles); cudaFree(d.lines); cudaFree(d.raw); cudaFree(d.sincos);
         cudaFree(d.rec2); cudaFree(d.counter2); cudaFree(d.rq[0]); cudaFree(d.rq[1]); cudaFree(d.gstat[0]); cudaFree(d.gstat[1]); cudaFree(d.stats_scratch); cudaFree(d.dirtab);
         for (auto& a : d.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
         if (d.fork_ev) cudaEventDestroy(d.fork_ev);
@@ -749,7 +750,8 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
             Ml.force_tiles = ms.rect_smem > 200 * 1024 || getenv("ALTB_LINE_TILES") != nullptr;
             ts.P.rp = {map->n_theta, map->n_phi, Ml.force_tiles, map->map_mode == ALTB_MAP_TRACEONCE_COMPAT, Ml.det_R, Ml.det_Wr};
             if (int rc = ensure(d.lines, d.lines_cap, 2 * (uint64_t)std::max<uint64_t>(d.rec_cap, batch_rec))) return rc;
-            ts.P.lines = d.lines; ts.P.lines_cap = (uint32_t)std::min<uint64_t>(d.lines_cap / 2, 0xffffffffull);
+            if (int rc = ensure(d.raw, d.raw_cap, 2 * (uint64_t)batch_rec)) return rc;
+            ts.P.lines = d.raw; ts.P.lines_cap = (uint32_t)std::min<uint64_t>(d.raw_cap / 2, 0xffffffffull);
         }
         if (dsink) {
             ts.P.n_slots = (uint32_t)g.size();
@@ -764,11 +766,19 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
             const uint32_t n = (uint32_t)piece_len(ray_id0 + off, n_rays - off, cap);
             const LaunchSlot& L = ls[overlap ? (launch_no & 1) : 0];
             if (t_trace_ms) CK(cudaEventRecord(d.ev[0], L.st));
-            if (lsink) { ts.P.n_lines = L.counter + 2; CK(cudaMemsetAsync(L.counter + 2, 0, 2 * sizeof(unsigned int), L.st)); }
+            if (lsink) { ts.P.n_lines = L.counter + 1; CK(cudaMemsetAsync(L.counter + 1, 0, 3 * sizeof(unsigned int), L.st)); }     // [1] raw, [2] rect, [3] tile
             rc_all = run_trace(ctx, d, ts, dsink ? SINK_DIRECTION : (lsink ? SINK_LINES : SINK_RECORDS), ray_id0 + off, n, L.rec, L.counter, L.rq, L.gstat, L.st);
             if (!rc_all && t_trace_ms) CK(cudaEventRecord(d.ev[1], L.st));
-            if (!rc_all && lsink)
-                rc_all = run_line_kernels(ctx, d, ms, Ml, d.lines, ts.P.lines_cap, L.counter + 2, n, d_counts + (size_t)g[0] * nb, L.st);
+            if (!rc_all && lsink) {
+                const uint32_t lcap = (uint32_t)std::min<uint64_t>(d.lines_cap / 2, 0xffffffffull);
+                int cb = d.sm_count * 8;
+                const int need = (int)((n + 255) / 256);
+                if (cb > need) cb = need;
+                k_prepare_raw<<<cb, 256, 0, L.st>>>(d.raw, L.counter + 1, ts.P.rp, d.lines, lcap, L.counter + 2);
+                ctx->launches++;
+                CK(cudaGetLastError());
+                rc_all = run_line_kernels(ctx, d, ms, Ml, d.lines, lcap, L.counter + 2, n, d_counts + (size_t)g[0] * nb, L.st);
+            }
             else if (!rc_all && !dsink)
                 rc_all = run_map(ctx, d, msg, L.rec, L.counter, n, ray_id0 + off, d_counts + (size_t)g[0] * nb, d_stats + (size_t)g[0] * 8, nullptr, L.st);
             if (!rc_all && t_trace_ms) {

@@ -295,20 +295,17 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
     const unsigned lane = threadIdx.x & 31u;
     bool resume = false;
     QEntry e;
-    // LINES: an escaping ray that passes the port test leaves its test line here (0: nothing, 1: rectangle list, 2: tile list)
-    int line_kind = 0; f3 lL = {0.f, 0.f, 0.f}, lv = {0.f, 0.f, 0.f}; uint32_t lr1 = 0u, lr2 = 0u;
+    // LINES: an escaping ray that passes the port test leaves its end point and direction here; they are appended to the raw
+    // list after the divergent part (the candidate rectangles are k_prepare_raw's job: computed here -- acosf, asinf, atan2f --
+    // they made this rarely-run code large enough to evict the bounce loop from the instruction cache: "no instruction"
+    // stalls 0.19 -> 1.95 per issue, 15 % off the whole kernel)
+    bool line_out = false; f3 lL = {0.f, 0.f, 0.f}, lv = {0.f, 0.f, 0.f};
     auto exit_line = [&](float px, float py, float pz, float dx, float dy, float dz, uint32_t hits) {
         unsigned long long* gs = trace_stats(P, 1u, 0u);
         stat_end(gs, 0, hits);
         if (pz < P.k.exit_zf) {
             atomicAdd(gs + 1, 1ull);
-            if (P.rp.compat) {            // the line from the origin through the exit point (fluxAtObserverFast.C:1181)
-                const f3 pos = {px, py, pz};
-                const float inv = 1.0f / sqrtf(dot3(pos, pos));
-                lL = {0.f, 0.f, 0.f}; lv = {px * inv, py * inv, pz * inv};
-            } else { lL = {px, py, pz}; lv = {dx, dy, dz}; }
-            const bool rect = line_rects(P.rp, lL, lv, lr1, lr2);
-            line_kind = rect ? (lr1 ? 1 : 0) : 2;
+            line_out = true; lL = {px, py, pz}; lv = {dx, dy, dz};
         }
     };
     if (lane < take) {
@@ -349,22 +346,16 @@ __device__ __noinline__ uint32_t drain_crossings(const TraceParams& P, const Dra
             }
         }
     }
-    if (LINES) {                                        // append the test lines: one reservation per list and warp
-        const unsigned mr = __ballot_sync(FULL, line_kind == 1), mt = __ballot_sync(FULL, line_kind == 2);
-        if (mr | mt) {
-            unsigned base_r = 0, base_t = 0;
-            if (lane == 0) {
-                if (mr) base_r = atomicAdd(P.n_lines, (unsigned)__popc(mr));
-                if (mt) base_t = atomicAdd(P.n_lines + 1, (unsigned)__popc(mt));
-            }
-            base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
-            if (line_kind) {
-                const unsigned below = (1u << lane) - 1u;
-                // rectangle list from the front, tile list from the back of the same buffer
-                float4* dst = line_kind == 1 ? P.lines + 2 * (size_t)(base_r + __popc(mr & below))
-                                             : P.lines + 2 * ((size_t)P.lines_cap - 1 - (base_t + __popc(mt & below)));
+    if (LINES) {                                        // append to the raw list: one reservation per warp
+        const unsigned mo = __ballot_sync(FULL, line_out);
+        if (mo) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(P.n_lines, (unsigned)__popc(mo));
+            base = __shfl_sync(FULL, base, 0);
+            if (line_out) {
+                float4* dst = P.lines + 2 * (size_t)(base + __popc(mo & ((1u << lane) - 1u)));
                 dst[0] = make_float4(lL.x, lL.y, lL.z, lv.x);
-                dst[1] = make_float4(lv.y, lv.z, __uint_as_float(lr1), __uint_as_float(lr2));
+                dst[1] = make_float4(lv.y, lv.z, 0.f, 0.f);
             }
         }
     }
@@ -946,40 +937,64 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
 // records -> two dense lists of the escaping rays' test lines (L.xyz, v.x | v.yz, rect1, rect2) in ONE buffer: from the front
 // for the ray-stationary kernel, from the back (rectangle words unused) for the tile kernel.  Order is irrelevant (integer counts).
 // TRACEONCE_COMPAT: the line from the origin through the exit point (fluxAtObserverFast.C:1181).
+// one escaping ray (end point pos, direction dir) per lane with `pf` set -> its test line + rectangles, appended to the rectangle
+// list (front of `lines`) or the tile list (back); all 32 lanes of the warp call this together
+__device__ __forceinline__ void emit_line(const RectParams& RP, bool pf, const f3& pos, const f3& dir, float4* __restrict__ lines,
+                                          uint32_t lines_cap, unsigned int* __restrict__ n_lines) {
+    const unsigned lane = threadIdx.x & 31u;
+    bool rect = false; f3 L = {0.f, 0.f, 0.f}, v = {0.f, 0.f, 0.f}; uint32_t r1 = 0u, r2 = 0u;
+    if (pf) {
+        if (RP.compat) {                 // the line from the origin through the exit point (fluxAtObserverFast.C:1181)
+            const float inv = 1.0f / sqrtf(dot3(pos, pos));
+            L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
+        } else { L = pos; v = dir; }
+        rect = line_rects(RP, L, v, r1, r2);
+    }
+    const unsigned mr = __ballot_sync(FULL, pf && rect && r1 != 0u), mt = __ballot_sync(FULL, pf && !rect);
+    unsigned base_r = 0, base_t = 0;
+    if (lane == 0) {
+        if (mr) base_r = atomicAdd(n_lines, (unsigned)__popc(mr));
+        if (mt) base_t = atomicAdd(n_lines + 1, (unsigned)__popc(mt));
+    }
+    base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
+    if (pf && (!rect || r1 != 0u)) {
+        const unsigned below = (1u << lane) - 1u;
+        float4* dst = rect ? lines + 2 * (size_t)(base_r + __popc(mr & below))          // rectangle list from the front,
+                           : lines + 2 * ((size_t)lines_cap - 1 - (base_t + __popc(mt & below)));   // tile list from the back
+        dst[0] = make_float4(L.x, L.y, L.z, v.x);
+        dst[1] = make_float4(v.y, v.z, __uint_as_float(r1), __uint_as_float(r2));
+    }
+}
+
 __global__ void __launch_bounds__(256) k_prepare_lines(const altb_record* __restrict__ rec, uint32_t n, const MapParams M,
                                                        float4* __restrict__ lines, uint32_t lines_cap,
                                                        unsigned int* __restrict__ n_lines /* [0] rect, [1] tile */) {
     const RectParams RP = {M.n_theta, M.n_phi, M.force_tiles, M.mode == ALTB_MAP_TRACEONCE_COMPAT, M.det_R, M.det_Wr};
-    const unsigned lane = threadIdx.x & 31u;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        bool pf = false, rect = false; f3 pos, dir, L = {0.f, 0.f, 0.f}, v = {0.f, 0.f, 0.f}; uint32_t hits, status, r1 = 0u, r2 = 0u;
+        bool pf = false; f3 pos = {0.f, 0.f, 0.f}, dir = pos; uint32_t hits, status;
         if (i < n) {
             load_record(rec, i, pos, dir, hits, status);
             pf = port_flag(M.count_all, M.exit_zf, pos, status);
         }
-        if (pf) {
-            if (M.mode == ALTB_MAP_TRACEONCE_COMPAT) {
-                const float inv = 1.0f / sqrtf(dot3(pos, pos));
-                L = {0.f, 0.f, 0.f}; v = {pos.x * inv, pos.y * inv, pos.z * inv};
-            } else { L = pos; v = dir; }
-            rect = line_rects(RP, L, v, r1, r2);
+        emit_line(RP, pf, pos, dir, lines, lines_cap, n_lines);
+    }
+}
+
+// the same from the RAW list k_trace's LINES sink wrote (every entry is an escaping ray that passed the port test)
+__global__ void __launch_bounds__(256) k_prepare_raw(const float4* __restrict__ raw, const unsigned int* __restrict__ n_raw_ptr, const RectParams RP,
+                                                     float4* __restrict__ lines, uint32_t lines_cap, unsigned int* __restrict__ n_lines) {
+    const size_t n = *n_raw_ptr;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n_pad = (n + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        f3 pos = {0.f, 0.f, 0.f}, dir = pos;
+        if (i < n) {
+            const float4 a = __ldg(raw + 2 * i), b = __ldg(raw + 2 * i + 1);
+            pos = {a.x, a.y, a.z}; dir = {a.w, b.x, b.y};
         }
-        const unsigned mr = __ballot_sync(FULL, pf && rect && r1 != 0u), mt = __ballot_sync(FULL, pf && !rect);
-        unsigned base_r = 0, base_t = 0;
-        if (lane == 0) {
-            if (mr) base_r = atomicAdd(n_lines, (unsigned)__popc(mr));
-            if (mt) base_t = atomicAdd(n_lines + 1, (unsigned)__popc(mt));
-        }
-        base_r = __shfl_sync(FULL, base_r, 0); base_t = __shfl_sync(FULL, base_t, 0);
-        if (pf && (!rect || r1 != 0u)) {
-            const unsigned below = (1u << lane) - 1u;
-            float4* dst = rect ? lines + 2 * (size_t)(base_r + __popc(mr & below))          // rectangle list from the front,
-                               : lines + 2 * ((size_t)lines_cap - 1 - (base_t + __popc(mt & below)));   // tile list from the back
-            dst[0] = make_float4(L.x, L.y, L.z, v.x);
-            dst[1] = make_float4(v.y, v.z, __uint_as_float(r1), __uint_as_float(r2));
-        }
+        emit_line(RP, i < n, pos, dir, lines, lines_cap, n_lines);
     }
 }
 
