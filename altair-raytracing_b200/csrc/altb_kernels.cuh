@@ -114,32 +114,61 @@ __device__ __forceinline__ LineRect unpack_rect(uint32_t u) { return {(int)(u & 
 static constexpr int RECT_MAX_BINS = 8192;          // larger rectangles: the tile kernel culls better
 static constexpr int RECT_MAX_DIM = 255;            // 8-bit fields
 
-// (theta, phi) bounding rectangle of the cap of angular radius alpha (sin / cos given) about the unit direction u (relative
-// to c0, z up): false if no bin centre of the lower hemisphere can lie in it
-__device__ __forceinline__ bool cap_rect(const RectParams& M, float ux, float uy, float uz, float alpha, LineRect& r) {
+// columns whose centre lies within +-hw of the azimuth pc (hw >= pi: the whole ring)
+__device__ __forceinline__ bool phi_range(const RectParams& M, float pc, float hw, int& j0, int& nj) {
+    j0 = 0; nj = M.n_phi;
+    if (hw >= 3.1415f) return true;
+    const float d = hw * 1.002f + 1e-4f, inv_dph = (float)M.n_phi * 0.15915494f;
+    const int jlo = (int)ceilf((pc - d) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + d) * inv_dph - 0.5f + 1e-3f);
+    nj = jhi - jlo + 1;
+    if (nj <= 0) return false;
+    if (nj < M.n_phi) { j0 = jlo % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
+    return true;
+}
+
+// (theta, phi) bounding rectangle(s) of the cap of angular radius alpha about the unit direction u (relative to c0, z up).
+// Returns the number of rectangles: 0 if no bin centre of the lower hemisphere can lie in the cap, 1 normally, 2 when the
+// cap contains or nearly touches the pole (allow_split): there the single rectangle is (nearly) the whole ring over all its
+// rows, although beyond the pole region the cap narrows quickly -- the far rows get their own, narrower column range (half
+// width of the cap at the split row, by the spherical law of cosines).  Rays within 12 deg of the axis are 4 % of the
+// escaping rays but a quarter of all tests; the split saves 7 % of the tests overall.
+__device__ __forceinline__ int cap_rect(const RectParams& M, float ux, float uy, float uz, float alpha, bool allow_split, LineRect& r, LineRect& rf) {
     const float HALF_PI = 1.5707964f;
-    const float thc = acosf(fminf(fmaxf(-uz, -1.0f), 1.0f));
+    const float cz = fminf(fmaxf(-uz, -1.0f), 1.0f);
+    const float thc = acosf(cz);
     const float tlo = thc - alpha, thi = thc + alpha;
-    if (tlo >= HALF_PI) return false;
+    if (tlo >= HALF_PI) return 0;
     const float inv_dth = (float)M.n_theta * (1.0f / HALF_PI);
     int i0 = (int)ceilf(tlo * inv_dth - 0.5f - 1e-3f), i1 = (int)floorf(thi * inv_dth - 0.5f + 1e-3f);
     i0 = max(i0, 0); i1 = min(i1, M.n_theta - 1);
-    if (i1 < i0) return false;
+    if (i1 < i0) return 0;
     // whole row PAIRS (2k, 2k+1): the pair kernel tests two neighbouring theta rows of one column per lane
     i0 &= ~1; i1 |= 1;
-    int j0 = 0, nj = M.n_phi;
-    const float sa = sinf(alpha), sc = sinf(thc);
-    if (thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha) {
-        const float dphi = asinf(sa / sc) * 1.002f + 1e-4f;
-        const float pc = atan2f(uy, ux);
-        const float inv_dph = (float)M.n_phi * 0.15915494f;
-        const int jlo = (int)ceilf((pc - dphi) * inv_dph - 0.5f - 1e-3f), jhi = (int)floorf((pc + dphi) * inv_dph - 0.5f + 1e-3f);
-        nj = jhi - jlo + 1;
-        if (nj <= 0) return false;
-        if (nj < M.n_phi) { j0 = jlo % M.n_phi; if (j0 < 0) j0 += M.n_phi; } else nj = M.n_phi;
-    }
+    const float sa = sinf(alpha), ca = cosf(alpha), sc = sinf(thc);
+    const bool ring = !(thc > alpha && sa < sc * 0.999f && thi < 3.1415927f - alpha);
+    const float hw1 = ring ? 4.0f : asinf(sa / sc);
+    const float pc = atan2f(uy, ux);
+    int j0, nj;
+    if (!phi_range(M, pc, hw1, j0, nj)) return 0;
     r = {i0, i1 - i0 + 1, j0, nj};
-    return true;
+    if (!allow_split || hw1 < 1.309f) return 1;                     // narrower than +-75 deg: one rectangle
+    // split row: 30 % of the way from where the ring stops being complete to the far edge of the cap
+    const float tfull = thc <= alpha ? alpha - thc : fmaxf(tlo, 0.0f);
+    const int is = (int)rintf((tfull + 0.3f * (thi - tfull)) * inv_dth) & ~1;
+    if (is < i0 + 2 || is >= i1) return 1;
+    const float ts = (float)is / inv_dth;                           // lower edge of the far rows
+    // the cap is widest at theta* = acos(cos(thc) / cos(alpha)): the far part must lie beyond it for its lower edge to bound it
+    if (fabsf(cz) < ca && acosf(cz / ca) > ts) return 1;
+    const float den = sinf(ts) * sc;
+    if (!(den > 1e-6f)) return 1;
+    const float c = (ca - cosf(ts) * cz) / den;
+    if (c <= -0.98f) return 1;                                      // still (nearly) the whole ring at the split row
+    const float hw2 = c >= 1.0f ? 0.0f : acosf(c);
+    int j0f, njf;
+    r.ni = is - i0;
+    if (!phi_range(M, pc, hw2, j0f, njf)) return 1;                 // nothing beyond the split row
+    rf = {is, i1 - is + 1, j0f, njf};
+    return 2;
 }
 
 // One escaping ray's test line -> 0, 1 or 2 rectangles.  Returns false when the ray must go to the tile kernel.
@@ -163,9 +192,25 @@ __device__ __forceinline__ bool line_rects(const RectParams& M, const f3& L, con
     if (!(chord < R)) return false;
     const float alpha = 2.0f * asinf(chord / (2.0f * R)) + 1e-4f;
     const float invR = 1.0f / R;
-    LineRect a, b;
-    const bool ha = cap_rect(M, (m.x + tp * vh.x) * invR, (m.y + tp * vh.y) * invR, (m.z + tp * vh.z) * invR, alpha, a);
-    const bool hb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, (m.z - tp * vh.z) * invR, alpha, b);
+    LineRect a, b, af, bf;
+    // both caps in the lower hemisphere (rare): one rectangle each; otherwise the one cap may use both words (polar split)
+    const float ubz = (m.z - tp * vh.z) * invR, uaz = (m.z + tp * vh.z) * invR;
+    const float reach = cosf(fminf(1.5707964f + alpha, 3.1415927f));         // -u.z below this: the cap cannot reach theta < 90 deg
+    const bool a_only = -ubz <= reach, b_only = -uaz <= reach;
+    const int na = cap_rect(M, (m.x + tp * vh.x) * invR, (m.y + tp * vh.y) * invR, uaz, alpha, a_only, a, af);
+    const int nb = cap_rect(M, (m.x - tp * vh.x) * invR, (m.y - tp * vh.y) * invR, ubz, alpha, b_only && na == 0, b, bf);
+    const bool ha = na > 0, hb = nb > 0;
+    if (na == 2 && !hb) {
+        if (a.ni * a.nj + af.ni * af.nj > RECT_MAX_BINS) return false;
+        r1 = pack_rect(a); r2 = pack_rect(af);
+        return true;
+    }
+    if (nb == 2 && !ha) {
+        if (b.ni * b.nj + bf.ni * bf.nj > RECT_MAX_BINS) return false;
+        r1 = pack_rect(b); r2 = pack_rect(bf);
+        return true;
+    }
+    if (na == 2) { a.ni += af.ni; }                                 // (cannot happen: a split needs the other cap out of reach) undo
     if (ha && hb) {
         // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
         // (rays that leave almost sideways: both caps straddle the equator, 180 deg apart in phi -- they share rows, not columns)
