@@ -102,21 +102,35 @@ altb_source makeSource(double x, double y, double z, double dx, double dy, doubl
     return s;
 }
 
+// One library context per device count, kept for the life of the process: the reference builds and deletes an AOpticsManager
+// per macro call, but a context owns device buffers (records, line lists) and, with several GPUs, NCCL communicators --
+// sweepSeries (25 calls) would otherwise allocate and free them 25 times.  Single host thread, as the reference.
+struct CtxCache {
+    altb_ctx* h[65] = {nullptr};
+    void release() { for (auto& c : h) if (c) { altb_destroy(c); c = nullptr; } }
+    // no destructor on purpose: at static-destruction time the CUDA runtime may already be gone; altbm_release() frees explicitly
+};
+CtxCache& ctx_cache() { static CtxCache c; return c; }
+
 struct Ctx {
     altb_ctx* h = nullptr;
     explicit Ctx(int threads) {
-        // the reference's (unused) `threads` argument selects how many GPUs of this process work on the rays
+        // the reference's `threads` argument (SetMaxThreads) selects how many GPUs of this process work on the rays
         int n = altb_device_count();
         if (threads > 0 && threads < n) n = threads;
-        if (altb_create(&h, nullptr, n > 0 ? n : 1) != 0) {
-            std::cerr << "Error: " << altb_last_error() << std::endl;
-            h = nullptr;
+        if (n < 1) n = 1;
+        if (n > 64) n = 64;
+        altb_ctx*& slot = ctx_cache().h[n];
+        if (!slot) {
+            if (altb_create(&slot, nullptr, n) != 0) {
+                std::cerr << "Error: " << altb_last_error() << std::endl;
+                slot = nullptr;
+            }
+            // 2^26-ray launches (2 GiB of records) are plenty for the macros' ray counts; the library default (2^28) is for long runs
+            else altb_set_batch(slot, 1ull << 26);
         }
-        // a macro call makes and drops its own context: 2^26-ray launches (2 GiB of records) keep the allocation and its
-        // release cheap; the library default (2^28) only pays off for long-lived contexts
-        if (h) altb_set_batch(h, 1ull << 26);
+        h = slot;
     }
-    ~Ctx() { if (h) altb_destroy(h); }
 };
 
 void fillFluxMap(TH2D* h, const std::vector<uint64_t>& counts, int nTheta, int nPhi, double n) {
@@ -566,6 +580,7 @@ void distributionSphereDetectorSweep() {
 
 // ------------------------------------------------------------------ C entry points (ctypes / tests / other hosts)
 extern "C" {
+void altbm_release() { ctx_cache().release(); }       // free the cached library contexts (device buffers, NCCL communicators)
 int altbm_set(const char* key, double v) {
     Settings& S = settings();
     std::string k = key;
