@@ -48,7 +48,7 @@ static constexpr int ST_CROSSING = 100;
 // everything that involves the port edge happens in the kernel's slow path.
 // zcf = the port plane R1 cos(theta_max) of the ray's scene (k.zc for single-scene launches; per lane in batched ones).
 template <bool ROUGH, int MODEL, bool DEFER_CROSSING, int C = CONTRACT_EXACT>
-__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, float zcf, const DrawTabs& T, RayState& s, const HitDraws& dr) {
+__device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, float zcf, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
     if (DEFER_CROSSING || s.where == EV_WALL) {
@@ -210,7 +210,6 @@ __device__ __forceinline__ bool line_rects(const RectParams& M, const f3& L, con
         r1 = pack_rect(b); r2 = pack_rect(bf);
         return true;
     }
-    if (na == 2) { a.ni += af.ni; }                                 // (cannot happen: a split needs the other cap out of reach) undo
     if (ha && hb) {
         // both caps reach the lower hemisphere (lines near the equator): rectangles that share bins would count hits twice
         // (rays that leave almost sideways: both caps straddle the equator, 180 deg apart in phi -- they share rows, not columns)
@@ -323,7 +322,7 @@ __device__ __noinline__ int edge_bounces(const TraceParams& P, const Geom& g, co
         HitDraws dr;
         hit_from_philox<NEED_G, C>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, t.hits, dr);
         if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, t.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false, C>(g, P.k, (float)g.zc, T, t, dr);
+        st = bounce_step<ROUGH, MODEL, false, C>(g, P.k, (float)g.zc, t, dr);
     } while (st == 0 && t.where != EV_WALL);
     return st;
 }
@@ -529,7 +528,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
                 const uint32_t ctr_lo = P.ctr_lo0 + (BATCHED ? idx & imask : idx);
                 hit_from_philox<NEED_G, C>(P.keys, T, P.k.abs_thr, P.k.spec_thr, ctr_lo, P.ctr_hi, s.hits, dr);
                 if (MODEL == 3) dr.u_r = lobe_accept(P.keys, ctr_lo, P.ctr_hi, s.hits, P.k.lobe_n, P.k.lobe_ang);
-                const int st = bounce_step<ROUGH, MODEL, true, C>(P.g, P.k, BATCHED ? zc : P.k.zc, T, s, dr);
+                const int st = bounce_step<ROUGH, MODEL, true, C>(P.g, P.k, BATCHED ? zc : P.k.zc, s, dr);
                 if (st == ST_CROSSING) { crossing = true; alive = false; }
                 else if (st) {
                     if (SINK == SINK_RECORDS) store_record(rec, idx, s, st);
@@ -603,7 +602,7 @@ __global__ void __launch_bounds__(128) k_trace_generic(const __grid_constant__ T
         const uint64_t rid = P.ray_id0 + i;
         hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), s.hits, dr);
         if (MODEL == 3) dr.u_r = lobe_accept(P.keys, rid, s.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, T, s, dr);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, s, dr);
     }
     store_record(rec, i, s, st);
 }
@@ -666,7 +665,7 @@ __global__ void __launch_bounds__(128) k_replay(const __grid_constant__ ReplayPa
         dr.u_psi = b.x; dr.g0 = b.y; dr.g1 = b.z; dr.u_spare = b.w;
         HitDraws h;
         hit_from_draws<FULL_AZ>(dr, P.k.rho, P.k.p_spec, T, h);
-        st = bounce_step<ROUGH, MODEL, false, C>(P.g, P.k, P.k.zc, T, s, h);
+        st = bounce_step<ROUGH, MODEL, false, C>(P.g, P.k, P.k.zc, s, h);
     }
     store_record(rec, i, s, st);
 }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) k_trace_paths(const __grid_constant__ Tra
         const uint64_t rid = P.ray_id0 + i;
         hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), s.hits, dr);
         if (MODEL == 3) dr.u_r = lobe_accept(P.keys, rid, s.hits, P.k.lobe_n, P.k.lobe_ang);
-        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, T, s, dr);
+        st = bounce_step<ROUGH, MODEL, false>(P.g, P.k, P.k.zc, s, dr);
     }
     if (st == ALTB_EXITED) put(s.pos);
     npts[i] = np_;
