@@ -116,7 +116,7 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     g.lambertian = sc->lambertian; g.brdf_kind = sc->brdf_kind;
     g.max_bounces = sc->max_bounces; g.count_all = sc->count_all_status;
     double ps = 0.0, bs = 0.0;
-    if (sc->brdf_kind == 1) {
+    if (sc->brdf_kind == 1 || sc->brdf_kind == 3) {
         const double sum = sc->brdf_param[1] + sc->brdf_param[2];
         if (!(sum > 0)) return fail(ALTB_E_SCENE, "scene: brdf specular+diffuse must be > 0");
         ps = sc->brdf_param[1] / sum;
@@ -130,7 +130,7 @@ static int make_geom(const altb_scene* sc, Geom& g, KConsts& k) {
     k.lobe_ang = (float)(sc->brdf_kind == 2 ? sc->brdf_param[1] * PI_D / 180.0 : 0.0);
     k.rho = (float)sc->reflectance; k.sigma = (float)sc->roughness_rad;
     k.two_r1 = (float)(2.0 * g.R1); k.neg_inv_r1 = (float)(-1.0 / g.R1); k.nr_c = (float)(-0.5 / g.R1sq);
-    k.zc = (float)g.zc; k.p_spec = (float)ps; k.brdf_s = (float)bs; k.exit_zf = (float)g.exit_z;
+    k.zc = (float)g.zc; k.p_spec = (float)ps; k.brdf_s = (float)bs; k.exit_zf = (float)g.exit_z; k.inv_r2 = (float)(1.0 / g.R2);
     // integer forms of the two comparisons (u_abs = k 2^-24, u_sel = k 2^-14 are exact in f32):
     //   rho < u_abs   <=>  k > floor(rho 2^24)  <=>  w0 > (floor(rho 2^24) << 8 | 0xff)      (w0 = k << 8 | low byte)
     //   u_sel < p     <=>  k < ceil(p 2^14)
@@ -291,7 +291,7 @@ static int ensure(T*& p, uint64_t& cap, uint64_t need) {
 }
 
 // ---------------------------------------------------------------------------------- trace launch
-struct TraceSetup { TraceParams P; bool rough; int model; };
+struct TraceSetup { TraceParams P; bool rough; int model; bool rescatter; };   // rescatter: brdf_kind 3 (k_rescatter after the Lambertian trace)
 
 static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t seed, TraceSetup& ts) {
     memset(&ts.P, 0, sizeof ts.P);
@@ -303,6 +303,8 @@ static int setup_trace(const altb_scene* sc, const altb_source* src, uint64_t se
     ts.P.keys = philox_expand(seed);
     ts.rough = sc->roughness_rad != 0.0;
     ts.model = !sc->lambertian ? 2 : (sc->brdf_kind == 1 ? 1 : (sc->brdf_kind == 2 ? 3 : 0));
+    ts.rescatter = sc->brdf_kind == 3;
+    if (ts.rescatter && !sc->lambertian) return fail(ALTB_E_SCENE, "scene: brdf_kind 3 (post-hoc re-scatter) needs lambertian = 1");
     // one slot: this scene
     ts.P.n_slots = 1;
     ts.P.slots[0].zc = ts.P.g.zc; ts.P.slots[0].T2 = ts.P.g.T2; ts.P.slots[0].cth = ts.P.g.cth; ts.P.slots[0].sth = ts.P.g.sth;
@@ -379,6 +381,17 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
                      unsigned int* counter, QEntry* rq, unsigned long long* gstat, cudaStream_t st) {
     if (n == 0) return 0;
     TraceParams& P = ts.P;
+    if (ts.rescatter) {         // brdf_kind 3: the second stage works on the records of the first
+        if (sink != SINK_RECORDS) return fail(ALTB_E_ARG, "run_trace: brdf_kind 3 goes through the record path");
+        P.ray_id0 = ray_id0; P.n = n; P.sincos = d.sincos;
+    }
+    auto rescatter = [&]() -> int {
+        if (ts.rough) k_rescatter<true><<<(n + 127) / 128, 128, 0, st>>>(P, rec);
+        else k_rescatter<false><<<(n + 127) / 128, 128, 0, st>>>(P, rec);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    };
     if (P.kind0 == EV_EXIT) {   // the source points straight out of the port: every ray is the same record
         altb_record proto;
         for (int i = 0; i < 3; i++) { proto.pos[i] = (float)P.x0[i]; proto.dir[i] = (float)P.d0[i]; }
@@ -389,7 +402,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         else k_fill_records<<<d.sm_count * 4, 256, 0, st>>>(rec, n, proto);
         ctx->launches++;
         CK(cudaGetLastError());
-        return 0;
+        return ts.rescatter ? rescatter() : 0;
     }
     P.ray_id0 = ray_id0; P.ctr_lo0 = (uint32_t)ray_id0; P.ctr_hi = (uint32_t)(ray_id0 >> 32);
     P.n = n;
@@ -433,7 +446,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    return 0;
+    return ts.rescatter ? rescatter() : 0;
 }
 
 // [off, off+len) pieces of a ray-id range: at most `cap` rays each, none straddling a multiple of 2^32 of the GLOBAL id
@@ -699,9 +712,9 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
     }
     // ---- plan: which scenes share launches
     const bool dir_mode = map->map_mode == ALTB_MAP_DIRECTION;
-    auto dir_sink_ok = [&](int s) { return dir_mode && !tss[s].P.g.count_all && (tss[s].P.kind0 == EV_WALL || tss[s].P.kind0 == EV_EXIT); };
+    auto dir_sink_ok = [&](int s) { return dir_mode && !tss[s].rescatter && !tss[s].P.g.count_all && (tss[s].P.kind0 == EV_WALL || tss[s].P.kind0 == EV_EXIT); };
     const bool line_mode = map->map_mode == ALTB_MAP_LINE || map->map_mode == ALTB_MAP_TRACEONCE_COMPAT;
-    auto lines_sink_ok = [&](int s) { return line_mode && !tss[s].P.g.count_all && tss[s].P.kind0 == EV_WALL && !getenv("ALTB_LINE_RECORDS"); };
+    auto lines_sink_ok = [&](int s) { return line_mode && !tss[s].rescatter && !tss[s].P.g.count_all && tss[s].P.kind0 == EV_WALL && !getenv("ALTB_LINE_RECORDS"); };
     std::vector<std::vector<int>> groups;
     std::vector<char> seen((size_t)n_scenes, 0);
     for (int s = 0; s < n_scenes; s++) {
@@ -1073,6 +1086,7 @@ extern "C" int altb_replay_ex(altb_ctx* ctx, const altb_scene* scene, const doub
     CK(cudaSetDevice(d.dev));
     ReplayParams P;
     if (int rc = make_geom(scene, P.g, P.k)) return rc;
+    if (scene->brdf_kind == 3) return fail(ALTB_E_SCENE, "altb_replay: brdf_kind 3 (two rays per id) has no tape format");
     P.n = (uint32_t)n_rays; P.sincos = d.sincos;
     const bool rough = scene->roughness_rad != 0.0;
     const int model = !scene->lambertian ? 2 : (scene->brdf_kind == 1 ? 1 : (scene->brdf_kind == 2 ? 3 : 0));
@@ -1244,6 +1258,7 @@ extern "C" int altb_trace_paths(altb_ctx* ctx, const altb_scene* scene, const al
     CK(cudaSetDevice(d.dev));
     TraceSetup ts;
     if (int rc = setup_trace(scene, src, seed, ts)) return rc;
+    if (ts.rescatter) return fail(ALTB_E_SCENE, "altb_trace_paths: a polyline is ONE ray; brdf_kind 3 traces two per id");
     ts.P.ray_id0 = ray_id0; ts.P.n = (uint32_t)n_rays; ts.P.chunk = 0; ts.P.sincos = d.sincos;
     float* d_pts = nullptr; uint32_t* d_np = nullptr; uint8_t* d_st = nullptr;
     const size_t nb = (size_t)n_rays * max_points * 3 * sizeof(float);

@@ -14,7 +14,7 @@
 
 namespace altb {
 
-enum { EV_WALL = 1, EV_EDGE = 2, EV_EXIT = 3 };
+enum { EV_WALL = 1, EV_EDGE = 2, EV_EXIT = 3, EV_OUTER = 4 };   // OUTER: the shell's outer surface hit from outside (brdf_kind 3 only)
 
 struct Geom {
     double R1, R2, R1sq, R2sq, zc, T2, cth, sth, H, exit_z;
@@ -22,7 +22,7 @@ struct Geom {
 };
 
 struct KConsts {
-    float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang; int lobe_n;
+    float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, exit_zf, lobe_ang, inv_r2; int lobe_n;
     int tilt_small, spec_small;   // sigma * max|g| <= 0.9 / brdf_s * max|g| <= 0.9: sin/cos without the quadrant reduction (tilt_small = 2: <= 0.06)
     uint32_t abs_thr, spec_thr;   // integer forms of "rho < u_abs" / "u_sel < p_spec" (altb_math.cuh: HitDraws)
 };
@@ -143,6 +143,66 @@ ALTB_HD int from_edge(const Geom& g, const double* q, const double* d, double* o
         return cap_crossing(g, h, d, out);
     }
     box_exit(g, q, d, out);
+    return EV_EXIT;
+}
+
+// brdf_kind 3 (nonLambertianFlux.C:265-268): the re-scattered ray starts where the primary ray ended -- on the world box,
+// OUTSIDE the shell -- with any direction.  First event: the solid outer surface S2 (OUTER), or, through the opening of S2,
+// the conical port edge (EDGE) or -- across the cavity -- the inner wall (WALL); otherwise it leaves (EXIT, out = world-box
+// point; a ray that starts on the box heading outward ends where it starts).
+ALTB_HD int from_outside(const Geom& g, const double* p, const double* d, double* out) {
+    const double b = (p[0] * d[0] + p[1] * d[1]) + p[2] * d[2];
+    const double c2 = ((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]) - g.R2sq;
+    if (b < 0.0 && c2 > 0.0) {
+        const double disc = b * b - c2;
+        if (disc > 0.0) {
+            const double s2 = -b - sqrt(disc);
+            const double x[3] = {p[0] + s2 * d[0], p[1] + s2 * d[1], p[2] + s2 * d[2]};
+            if (x[2] >= g.R2 * g.cth) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return EV_OUTER; }
+            // x is inside the opening cone: first crossing of the cone (cf. cap_crossing) ...
+            const double A = (d[0] * d[0] + d[1] * d[1]) - g.T2 * (d[2] * d[2]);
+            const double B = (x[0] * d[0] + x[1] * d[1]) - g.T2 * (x[2] * d[2]);
+            const double C = (x[0] * x[0] + x[1] * x[1]) - g.T2 * (x[2] * x[2]);
+            const double dc = B * B - A * C;
+            double s_c = INFINITY, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            if (dc >= 0.0) {
+                const double sq = sqrt(dc);
+                double s = 0.0;
+                bool have = false;
+                if (B > 0.0) { const double den = B + sq; if (den > 0.0) { s = -C / den; have = true; } }
+                else if (A > 0.0) { s = (sq - B) / A; have = true; }
+                if (have && s > 0.0) {
+                    q0 = x[0] + s * d[0]; q1 = x[1] + s * d[1]; q2 = x[2] + s * d[2];
+                    if (q2 < 0.0) {
+                        const double r2 = (q0 * q0 + q1 * q1) + q2 * q2;
+                        if (r2 >= g.R1sq && r2 <= g.R2sq) s_c = s;
+                    }
+                }
+            }
+            // ... against the entry into the cavity through the cap of S1
+            double s_in = INFINITY;
+            const double b1 = (x[0] * d[0] + x[1] * d[1]) + x[2] * d[2];
+            const double c1 = ((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]) - g.R1sq;
+            if (b1 < 0.0) { const double d1 = b1 * b1 - c1; if (d1 > 0.0) s_in = -b1 - sqrt(d1); }
+            if (s_c < s_in) { out[0] = q0; out[1] = q1; out[2] = q2; return EV_EDGE; }
+            if (s_in < INFINITY) {
+                const double xin[3] = {x[0] + s_in * d[0], x[1] + s_in * d[1], x[2] + s_in * d[2]};
+                const double bb = (xin[0] * d[0] + xin[1] * d[1]) + xin[2] * d[2];
+                const double cc = ((xin[0] * xin[0] + xin[1] * xin[1]) + xin[2] * xin[2]) - g.R1sq;
+                double dd = bb * bb - cc;
+                if (dd < 0.0) dd = 0.0;
+                const double t = sqrt(dd) - bb;
+                double h[3] = {xin[0] + t * d[0], xin[1] + t * d[1], xin[2] + t * d[2]};
+                const double sc = g.R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+                h[0] *= sc; h[1] *= sc; h[2] *= sc;
+                if (h[2] >= g.zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+                return cap_crossing(g, h, d, out);
+            }
+            box_exit(g, x, d, out);
+            return EV_EXIT;
+        }
+    }
+    box_exit(g, p, d, out);
     return EV_EXIT;
 }
 

@@ -2,6 +2,7 @@
 //   K1  k_trace        persistent warps with ray regeneration: source -> bounce loop -> 32-byte record
 //       k_trace_generic  one thread per ray, for sources whose first event is the port rim
 //   K1r k_replay       same state machine, draws streamed from a recorded tape
+//   K1p k_rescatter    brdf_kind 3: one BRDF sample at the primary ray's last point + the second trace (nonLambertianFlux.C:246-268)
 //   K2a k_map_direction  records -> stats + one-bin-per-ray direction map (warp-compacted binning, shared-memory histogram)
 //   K2b k_prepare_lines + k_map_line_rect (ray-stationary: the cap of candidate bins as a (theta, phi) rectangle, packed
 //                      FP32 pair tests, shared-memory histogram) + k_map_line (tile-culled, bin-stationary; the rays whose
@@ -47,12 +48,15 @@ static constexpr int ST_CROSSING = 100;
 // DEFER_CROSSING is the hot loop of k_trace: the ray is on the inner sphere by construction (s.where is not looked at),
 // everything that involves the port edge happens in the kernel's slow path.
 // zcf = the port plane R1 cos(theta_max) of the ray's scene (k.zc for single-scene launches; per lane in batched ones).
-template <bool ROUGH, int MODEL, bool DEFER_CROSSING, int C = CONTRACT_EXACT>
+// OUTER (k_rescatter only): the ray may also sit on the shell's OUTER surface (EV_OUTER), from where it can only leave.
+template <bool ROUGH, int MODEL, bool DEFER_CROSSING, int C = CONTRACT_EXACT, bool OUTER = false>
 __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, float zcf, RayState& s, const HitDraws& dr) {
     s.hits += 1;
     f3 nrm;
     if (DEFER_CROSSING || s.where == EV_WALL) {
         nrm = scale3(k.neg_inv_r1, s.pos);
+    } else if (OUTER && s.where == EV_OUTER) {
+        nrm = scale3(k.inv_r2, s.pos);
     } else {
         double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z}, nn[3];
         edge_normal(g, q, nn);
@@ -94,6 +98,12 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k, floa
         const double xd[3] = {(double)x.x, (double)x.y, (double)x.z};
         const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
         kind = cap_crossing(g, xd, dd, out);
+    } else if (OUTER && s.where == EV_OUTER) {       // the shell is convex: from its outer surface the ray leaves
+        const double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z};
+        const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
+        box_exit(g, q, dd, out);
+        kind = EV_EXIT;
+        s.dir = d;
     } else {
         const double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z};
         const double dd[3] = {(double)d.x, (double)d.y, (double)d.z};
@@ -736,6 +746,41 @@ __global__ void __launch_bounds__(256) k_stats(const altb_record* __restrict__ r
         acc.add(hits, status, port_flag(count_all, exit_zf, pos, status));
     }
     flush_stats(acc, stats);
+}
+
+// ------------------------------------------------------------------------------------ K1p post-hoc re-scatter
+// brdf_kind 3 -- the committed macro literally (nonLambertianFlux.C:246-268): the records of a plain Lambertian trace come in;
+// every ray that EXITED is re-scattered ONCE where it ended (on the world box) with the spec/diffuse mixture of
+// nonLambertianFlux.C:147-208, normal = lastPoint.Unit() (:258), incident = the ray's INITIAL direction (:246-249), and traced
+// again from there (:265-268): most leave at once, a quarter cross the world to another face, 2.5e-4 meet the shell's outer
+// surface, fewer still find the port.  The record becomes the second ray's (n_hits = both rays').  Counter word 3 of the
+// Philox block keeps the streams apart: 4 = the re-scatter draw, 5 = the second trace.  One thread per ray, exact contract.
+template <bool ROUGH>
+__global__ void __launch_bounds__(128) k_rescatter(const __grid_constant__ TraceParams P, altb_record* __restrict__ rec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    f3 pos, dir; uint32_t hits1, status;
+    load_record(rec, i, pos, dir, hits1, status);
+    if (status != ALTB_EXITED) return;            // rays that ended on the wall stay what they are (the macro's scene has rho = 1: none)
+    const DrawTabs T = make_tabs(P.sincos);
+    const uint64_t rid = P.ray_id0 + i;
+    HitDraws dr;
+    hit_from_philox<true, CONTRACT_EXACT, 4u>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), 0u, dr);
+    const f3 n = scale3(rcp_c(sqrt_c(dot3(pos, pos))), pos);
+    const f3 inc = {P.d0f[0], P.d0f[1], P.d0f[2]};
+    const f3 d = brdf_mix<CONTRACT_EXACT>(n, inc, dr.spec, dr.u_r, dr.g1, dr.sc_phi, P.k.brdf_s, P.k.spec_small != 0);
+    const double pd[3] = {(double)pos.x, (double)pos.y, (double)pos.z}, dd[3] = {(double)d.x, (double)d.y, (double)d.z};
+    double out[3];
+    const int kind = from_outside(P.g, pd, dd, out);
+    RayState s;
+    s.pos = {(float)out[0], (float)out[1], (float)out[2]}; s.dir = d; s.hits = 0; s.where = kind;
+    int st = kind == EV_EXIT ? ALTB_EXITED : 0;
+    while (!st) {
+        hit_from_philox<ROUGH, CONTRACT_EXACT, 5u>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), s.hits, dr);
+        st = bounce_step<ROUGH, 0, false, CONTRACT_EXACT, true>(P.g, P.k, P.k.zc, s, dr);
+    }
+    s.hits += hits1;
+    store_record(rec, i, s, st);
 }
 
 // ------------------------------------------------------------------------------------ K2a direction map

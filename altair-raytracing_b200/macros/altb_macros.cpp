@@ -420,8 +420,9 @@ void legacySweep(bool nonLambertian) {
     }
     TH2D* fluxMap = newFluxMap("Detector Flux Map;#theta (deg);#phi (deg)", nThetaBins, nPhiBins);
     altb_scene scene = simpleScene(thetaMax, 101 * cm, 0.5);
-    if (nonLambertian) {      // "CustomMirror": gBRDF(0.3, 0.4, 0.6) applied at every bounce (CustomMirror)
-        scene.brdf_kind = 1; scene.brdf_param[0] = 0.3; scene.brdf_param[1] = 0.4; scene.brdf_param[2] = 0.6;
+    if (nonLambertian) {      // gBRDF(0.3, 0.4, 0.6) (nonLambertianFlux.C:211): once, after the trace, as the committed macro does
+        scene.brdf_kind = S.nonlambertian_posthoc ? 3 : 1;      // (:246-268) -- or at every bounce ("CustomMirror")
+        scene.brdf_param[0] = 0.3; scene.brdf_param[1] = 0.4; scene.brdf_param[2] = 0.6;
     }
     altb_source src = nonLambertian ? makeSource(-60 * cm, 0, -80 * cm, 5, 0, 0) : makeSource(-60 * cm, 0, -80 * cm, 5, 2, 0);
     altb_map_spec map = {nThetaBins, nPhiBins, 100 * cm, 10 * cm, ALTB_MAP_PER_POSITION, n};
@@ -593,6 +594,7 @@ int altbm_set(const char* key, double v) {
     else if (k == "sweep_dtheta") S.sweep_dtheta = v;
     else if (k == "distribution_rays") S.distribution_rays = (int)v;
     else if (k == "nonlambertian_rays") S.nonlambertian_rays = (int)v;
+    else if (k == "nonlambertian_posthoc") S.nonlambertian_posthoc = (int)v;
     else if (k == "next_ray_id") S.next_ray_id = (uint64_t)v;
     else if (k == "advance_ray_ids") S.advance_ray_ids = (int)v;
     else if (k == "seed") S.seed = (uint64_t)v;

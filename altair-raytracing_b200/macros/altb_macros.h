@@ -33,6 +33,9 @@ struct Settings {
     int sweep_rays = 100000;          // integratingSphereDetectorSweep.C:125
     int distribution_rays = 10000;    // distributionSphereDetectorSweep.C:57
     int nonlambertian_rays = 100000;  // nonLambertianFlux.C:311
+    int nonlambertian_posthoc = 1;    // 1: the committed macro literally -- Lambertian trace, ONE BRDF sample at the last point,
+                                      //    second trace (nonLambertianFlux.C:246-268; brdf_kind 3);
+                                      // 0: gBRDF at EVERY bounce ("CustomMirror", brdf_kind 1: the model of BASELINE config C3)
     double sweep_dtheta = 0.5;        // integratingSphereDetectorSweep.C:126
     uint64_t seed = 4357;             // TRandom3 default seed
     // The reference's gRandom keeps advancing from one macro call to the next, so repeated calls (the five repeats per port

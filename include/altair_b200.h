@@ -51,10 +51,15 @@ typedef struct {
     int32_t lambertian;           /* EnableLambertian; 0 = specular mirror */
     int32_t max_bounces;          /* AOpticsManager::SetLimit */
     int32_t brdf_kind;            /* 0 Lambert; 1 "CustomMirror" = per-bounce spec/diffuse mixture of
-                                     nonLambertianFlux.C:147-208; 2 cos^n lobe of 'nonLambertianFlux copy.C':31-70 */
+                                     nonLambertianFlux.C:147-208; 2 cos^n lobe of 'nonLambertianFlux copy.C':31-70;
+                                     3 the committed macro literally (nonLambertianFlux.C:246-268): Lambertian trace, then ONE
+                                     sample of the kind-1 mixture where the ray ended (normal = lastPoint.Unit(), incident =
+                                     the INITIAL direction) and a second Lambertian trace from there -- the per-ray result is
+                                     the second ray's, n_hits counts both.  Record path only (LINE-type / per-position maps,
+                                     per-ray results; a DIRECTION map also goes through records); no replay, no polylines */
     int32_t count_all_status;     /* 0: only exited rays can pass the port test (batch macros);
                                      1: any final status (single-ray macros, makeIntegratingSphereNRays.C:74-78) */
-    double brdf_param[4];         /* kind 1: roughness, specular, diffuse (gBRDF(0.3,0.4,0.6));
+    double brdf_param[4];         /* kind 1, 3: roughness, specular, diffuse (gBRDF(0.3,0.4,0.6));
                                      kind 2: exponent (integer 1..8; reference 2), max angle [deg] (reference 60) */
     double exit_z;                /* exitPortZ, -100 cm */
 } altb_scene;

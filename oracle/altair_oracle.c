@@ -16,6 +16,7 @@
 #define EV_WALL 1
 #define EV_EDGE 2
 #define EV_EXIT 3
+#define EV_OUTER 4      /* brdf_kind 3 only: the solid OUTER surface of the shell, hit from outside */
 #define PI_D 3.14159265358979323846
 
 /* ------------------------------------------------------------------ scene constants */
@@ -25,8 +26,8 @@ typedef struct {
     int lobe_n;           /* brdf_kind 2: integer exponent of the cos^n lobe */
 } geom;
 
-typedef struct { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang; } consts_f;
-typedef struct { double rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang; } consts_d;
+typedef struct { float rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang, inv_r2; } consts_f;
+typedef struct { double rho, sigma, two_r1, neg_inv_r1, nr_c, zc, p_spec, brdf_s, lobe_ang, inv_r2; } consts_d;
 
 static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
     if (!(sc->r_inner > 0) || !(sc->r_outer >= sc->r_inner) || !(sc->world_half > sc->r_outer)) return -1;
@@ -43,7 +44,7 @@ static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
     g->lambertian = sc->lambertian; g->brdf_kind = sc->brdf_kind;
     g->max_bounces = sc->max_bounces; g->count_all = sc->count_all_status;
     double ps = 0.0, bs = 0.0;
-    if (sc->brdf_kind == 1) {          /* nonLambertianFlux.C:156-159: normalise (spec,diff) */
+    if (sc->brdf_kind == 1 || sc->brdf_kind == 3) {   /* nonLambertianFlux.C:156-159: normalise (spec,diff) */
         double sum = sc->brdf_param[1] + sc->brdf_param[2];
         if (!(sum > 0)) return -1;
         ps = sc->brdf_param[1] / sum;
@@ -62,6 +63,7 @@ static int make_geom(const orc_scene* sc, geom* g, consts_f* kf, consts_d* kd) {
     kf->rho = (float)kd->rho; kf->sigma = (float)kd->sigma; kf->two_r1 = (float)kd->two_r1;
     kf->neg_inv_r1 = (float)kd->neg_inv_r1; kf->nr_c = (float)kd->nr_c; kf->zc = (float)kd->zc;
     kf->p_spec = (float)kd->p_spec; kf->brdf_s = (float)kd->brdf_s;
+    kd->inv_r2 = 1.0 / g->R2; kf->inv_r2 = (float)kd->inv_r2;
     return 0;
 }
 
@@ -164,6 +166,65 @@ static int launch(const geom* g, const double* p0, const double* dir, double* d0
     h[0] *= sc; h[1] *= sc; h[2] *= sc;
     if (h[2] >= g->zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
     return cap_crossing(g, h, d0, out);
+}
+
+/* brdf_kind 3 (nonLambertianFlux.C:265-268): the re-scattered ray starts where the primary ray ended -- on the world box,
+ * OUTSIDE the shell -- with any direction.  Its first event: the solid outer surface S2 (EV_OUTER), or, through the opening
+ * of S2, the conical port edge (EV_EDGE) or -- across the cavity -- the inner wall (EV_WALL); otherwise it leaves (EV_EXIT,
+ * out = world-box point; a ray that starts on the box heading outward ends where it starts). */
+static int from_outside(const geom* g, const double* p, const double* d, double* out) {
+    double b = (p[0] * d[0] + p[1] * d[1]) + p[2] * d[2];
+    double c2 = ((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]) - g->R2sq;
+    if (b < 0.0 && c2 > 0.0) {
+        double disc = b * b - c2;
+        if (disc > 0.0) {
+            double s2 = -b - sqrt(disc);
+            double x[3] = {p[0] + s2 * d[0], p[1] + s2 * d[1], p[2] + s2 * d[2]};
+            if (x[2] >= g->R2 * g->cth) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return EV_OUTER; }
+            /* x is inside the opening cone: first crossing of the cone (cf. cap_crossing) ... */
+            double A = (d[0] * d[0] + d[1] * d[1]) - g->T2 * (d[2] * d[2]);
+            double B = (x[0] * d[0] + x[1] * d[1]) - g->T2 * (x[2] * d[2]);
+            double C = (x[0] * x[0] + x[1] * x[1]) - g->T2 * (x[2] * x[2]);
+            double dc = B * B - A * C;
+            double s_c = INFINITY, q[3] = {0, 0, 0};
+            if (dc >= 0.0) {
+                double sq = sqrt(dc), s = 0.0;
+                int have = 0;
+                if (B > 0.0) { double den = B + sq; if (den > 0.0) { s = -C / den; have = 1; } }
+                else if (A > 0.0) { s = (sq - B) / A; have = 1; }
+                if (have && s > 0.0) {
+                    q[0] = x[0] + s * d[0]; q[1] = x[1] + s * d[1]; q[2] = x[2] + s * d[2];
+                    if (q[2] < 0.0) {
+                        double r2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+                        if (r2 >= g->R1sq && r2 <= g->R2sq) s_c = s;
+                    }
+                }
+            }
+            /* ... against the entry into the cavity through the cap of S1 */
+            double s_in = INFINITY;
+            double b1 = (x[0] * d[0] + x[1] * d[1]) + x[2] * d[2];
+            double c1 = ((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]) - g->R1sq;
+            if (b1 < 0.0) { double d1 = b1 * b1 - c1; if (d1 > 0.0) s_in = -b1 - sqrt(d1); }
+            if (s_c < s_in) { out[0] = q[0]; out[1] = q[1]; out[2] = q[2]; return EV_EDGE; }
+            if (s_in < INFINITY) {
+                double xin[3] = {x[0] + s_in * d[0], x[1] + s_in * d[1], x[2] + s_in * d[2]};
+                double bb = (xin[0] * d[0] + xin[1] * d[1]) + xin[2] * d[2];
+                double cc = ((xin[0] * xin[0] + xin[1] * xin[1]) + xin[2] * xin[2]) - g->R1sq;
+                double dd = bb * bb - cc;
+                if (dd < 0.0) dd = 0.0;
+                double t = sqrt(dd) - bb;
+                double h[3] = {xin[0] + t * d[0], xin[1] + t * d[1], xin[2] + t * d[2]};
+                double sc = g->R1 / sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+                h[0] *= sc; h[1] *= sc; h[2] *= sc;
+                if (h[2] >= g->zc) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; return EV_WALL; }
+                return cap_crossing(g, h, d, out);
+            }
+            box_exit(g, x, d, out);
+            return EV_EXIT;
+        }
+    }
+    box_exit(g, p, d, out);
+    return EV_EXIT;
 }
 
 /* ------------------------------------------------------------------ f32 primitives */
@@ -273,9 +334,13 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  *   w0: u_abs 24 b | 8 b -> u_sel (low byte)      w1: u_r 24 b | 8 b -> bm_u1 (low byte)
  *   w2: u_phi 20 b | 12 b -> bm_u1 (high bits)    w3: u_psi 13 b | bm_u2 13 b | 6 b -> u_sel (high bits)
  * (g0, g1) = Box-Muller of (bm_u1 in (0,1] with 20 bits, bm_u2 with 13 bits). */
-void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]) {
+static void draws_blk(uint64_t seed, uint64_t ray_id, uint32_t k, uint32_t blk, float out[ORC_DRAWS_PER_HIT]);
+void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]) { draws_blk(seed, ray_id, k, 0u, out); }
+/* counter word 3: 0 = the surface hits of the (primary) trace; 1, 2 = the cos^n rejection loop (orc_draws_lobe);
+ * 4 = the post-hoc re-scatter of brdf_kind 3 (k = 0), 5 = the surface hits of its second trace */
+static void draws_blk(uint64_t seed, uint64_t ray_id, uint32_t k, uint32_t blk, float out[ORC_DRAWS_PER_HIT]) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, 0u};
+    uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, blk};
     uint32_t w[4];
     orc_philox4x32_10(ctr, key, w);
     out[0] = (float)(w[0] >> 8) * 0x1p-24f;
@@ -385,6 +450,13 @@ static void run_ray(const geom* g, const consts_f* kf, const consts_d* kd, int p
             k++;
             st = bounce_f(g, kf, &s, dr);
         }
+        if (g->brdf_kind == 3 && st == ORC_EXITED && !(ts && ts->tape)) {     /* post-hoc re-scatter + second trace */
+            const uint32_t h1 = s.n_hits;
+            draws_blk(seed, ray_id, 0u, 4u, dr);
+            st = rescatter_f(g, kf, &s, d0, dr);
+            while (!st) { draws_blk(seed, ray_id, s.n_hits, 5u, dr); st = bounce_f(g, kf, &s, dr); }
+            s.n_hits += h1;
+        }
         if (tape_n) *tape_n = k;
         if (rec) {
             for (int i = 0; i < 3; i++) { rec->pos[i] = s.pos[i]; rec->dir[i] = s.dir[i]; }
@@ -405,6 +477,13 @@ static void run_ray(const geom* g, const consts_f* kf, const consts_d* kd, int p
             else orc_draws(seed, ray_id, k, dr);
             k++;
             st = bounce_d(g, kd, &s, dr);
+        }
+        if (g->brdf_kind == 3 && st == ORC_EXITED && !(ts && ts->tape)) {
+            const uint32_t h1 = s.n_hits;
+            draws_blk(seed, ray_id, 0u, 4u, dr);
+            st = rescatter_d(g, kd, &s, d0, dr);
+            while (!st) { draws_blk(seed, ray_id, s.n_hits, 5u, dr); st = bounce_d(g, kd, &s, dr); }
+            s.n_hits += h1;
         }
         if (tape_n) *tape_n = k;
         if (rec) {
@@ -826,6 +905,7 @@ int orc_trace_paths(const orc_scene* sc, const orc_source* src, uint64_t ray_id0
                     uint32_t max_points, float* pts, uint32_t* npts, uint8_t* status) {
     geom g; consts_f kf; consts_d kd;
     if (make_geom(sc, &g, &kf, &kd)) return -1;
+    if (g.brdf_kind == 3) return -1;                  /* polylines show ONE ARay: the two-ray post-hoc mode has none */
     double d0[3], x0[3];
     int kind0 = launch(&g, src->pos, src->dir, d0, x0);
     if (kind0 < 0) return -2;

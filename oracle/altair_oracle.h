@@ -35,6 +35,7 @@
  *                    (checkIntersection)
  *   trace-once map   flux_at_observer/fluxAtObserverFast.C:1164-1303
  *   BRDF mixture     flux_at_observer/nonLambertianFlux.C:147-208
+ *   post-hoc mode    flux_at_observer/nonLambertianFlux.C:235-304 (re-scatter at the last point + second trace)
  *   direction hists  distributionSphereDetectorSweep.C:74-99
  *   physical disk    integratingSphereDetectorSweep.C:134-172
  */
@@ -53,8 +54,11 @@ typedef struct {
     double reflectance, roughness_rad;
     int32_t lambertian;   /* 1: diffuse model selected by brdf_kind; 0: ideal specular mirror */
     int32_t max_bounces;  /* AOpticsManager::SetLimit */
-    int32_t brdf_kind;    /* 0 Lambert, 1 spec/diffuse mixture (nonLambertianFlux.C:147-208),
-                             2 cos^n lobe ('nonLambertianFlux copy.C':31-70) */
+    int32_t brdf_kind;    /* 0 Lambert, 1 spec/diffuse mixture (nonLambertianFlux.C:147-208) at every bounce,
+                             2 cos^n lobe ('nonLambertianFlux copy.C':31-70),
+                             3 the committed macro literally (nonLambertianFlux.C:246-268): Lambertian trace, ONE sample of
+                               the kind-1 mixture at the last point (normal = lastPoint.Unit(), incident = the INITIAL
+                               direction), second Lambertian trace from there; the record is the second ray's, n_hits the sum */
     int32_t count_all_status; /* 0: only EXITED rays can "pass the port" (batch macros read
                                  GetExited/GetStopped only); 1: any status (single-ray macros) */
     double brdf_param[4]; /* kind 1: roughness, specular, diffuse; kind 2: exponent (integer 1..8), max angle [deg] */

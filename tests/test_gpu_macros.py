@@ -155,6 +155,30 @@ def test_cli_runner(M, altb):
     assert rows.shape == (900, 3) and rows[:, 2].sum() > 0 and open(os.path.join(M.out, "fluxmap_data.csv")).readline() == "theta,phi,fraction\n"
 
 
+def test_nonLambertianFlux_posthoc_and_per_bounce(M, oracle):
+    """nonLambertianFlux::sweepDetector: by default the committed macro literally (post-hoc re-scatter, brdf_kind 3); with
+    nonlambertian_posthoc = 0 the BRDF at every bounce (brdf_kind 1).  Both against the oracle, bin for bin."""
+    rpp = 150
+    base = dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000, count_all_status=1,
+                brdf_param=(0.3, 0.4, 0.6, 0.0))
+    mp = oracle.map_spec(45, 20, 100.0, 10.0, oracle.MAP_PER_POSITION, rays_per_position=rpp)
+    M.altbm_set(b"nonlambertian_rays", rpp)
+    maps = {}
+    try:
+        for posthoc, kind in ((1, 3), (0, 1)):
+            M.altbm_set(b"nonlambertian_posthoc", posthoc)
+            M.altbm_nonLambertianFlux_sweepDetector()
+            rows = _rows(os.path.join(M.out, "fluxmap_data.csv"))
+            counts, _ = oracle.fluxmap(oracle.scene(brdf_kind=kind, **base), oracle.source((-60, 0, -80), (5, 0, 0)), 900 * rpp, mp,
+                                       seed=4357, prec=oracle.F32)
+            assert rows.shape == (900, 3) and counts.sum() > 0
+            assert np.array_equal(np.rint(rows[:, 2] * rpp).astype(np.uint64), counts), kind
+            maps[kind] = counts
+        assert not np.array_equal(maps[1], maps[3])
+    finally:
+        M.altbm_set(b"nonlambertian_rays", 100000); M.altbm_set(b"nonlambertian_posthoc", 1)
+
+
 def test_full_size_sweepDetector_against_reference_map(M, altb):
     """BASELINE-size statistical parity on the GPU: the production macro (fluxAtObserverOptimize.C sweepDetector:
     16 200 positions x 50 000 fresh rays = 8.1e8 rays; 12 524 s in the reference's own footer) against the reference's

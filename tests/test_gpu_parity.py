@@ -36,6 +36,16 @@ def _scenes(mod):
         "cos2_lobe": dict(theta_max=170.0, brdf_kind=2, brdf_param=(2.0, 60.0, 0.0, 0.0)),     # 'nonLambertianFlux copy.C':31-70
         "cos5_lobe_smooth": dict(theta_max=166.0, brdf_kind=2, brdf_param=(5.0, 45.0, 0.0, 0.0), roughness=0.0, reflectance=1.0,
                                  max_bounces=10000),
+        # brdf_kind 3: the committed nonLambertianFlux.C literally (:213-226 scene, :246-268 re-scatter + second trace)
+        "c1_posthoc_macro": dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000,
+                                 count_all_status=1, brdf_kind=3, brdf_param=(0.3, 0.4, 0.6, 0.0)),
+        # ... small world, thick shell, all-specular lobe: 11 % of the second rays meet the shell again (outer surface, port
+        # edge, cavity: up to ~50 more hits), absorbed primaries stay as they are
+        "posthoc_stress": dict(theta_max=140.0, world_half=103.0, r_outer=102.5, reflectance=0.95, roughness=0.2,
+                               count_all_status=1, brdf_kind=3, brdf_param=(1.0, 1.0, 0.0, 0.0)),
+        # ... the source looks straight out of the port (every primary is the same record), no roughness
+        "posthoc_all_exit": dict(theta_max=120.0, world_half=110.0, reflectance=0.9, roughness=0.0, brdf_kind=3,
+                                 brdf_param=(0.3, 0.4, 0.6, 0.0)),
     }
 
 
@@ -96,7 +106,8 @@ def test_lobe_draws_bit_exact(ctx, oracle):
 @pytest.mark.parametrize("name", ["c2_lambert_rough", "c1_rho1_sigma0", "c3_custom_mirror", "specular",
                                   "big_port_160", "thick_shell", "rough_half", "suspended_limit_7", "limit_1",
                                   "tiny_port_178", "huge_port_100", "black_wall", "all_specular_lobe",
-                                  "all_diffuse_lobe", "mirror_sphere", "small_world", "cos2_lobe", "cos5_lobe_smooth"])
+                                  "all_diffuse_lobe", "mirror_sphere", "small_world", "cos2_lobe", "cos5_lobe_smooth",
+                                  "c1_posthoc_macro", "posthoc_stress", "posthoc_all_exit"])
 def test_trace_records_bit_exact(ctx, oracle, altb, name):
     kw = _scenes(altb)[name]
     n = 100_000
@@ -118,6 +129,33 @@ def test_trace_records_bit_exact(ctx, oracle, altb, name):
     for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
         assert g_st[key] == o_st[key], key
     assert g_st["n_exited"] + g_st["n_absorbed"] + g_st["n_suspended"] == n      # conservation
+    if name == "posthoc_stress":     # the second trace really ran: more hits than the plain Lambertian trace of the same ids
+        p_rec, _ = ctx.trace_records(altb.scene(**dict(kw, brdf_kind=0)), altb.source(src, direction), n, seed=SEED)
+        extra = g_rec["n_hits"].astype(np.int64) - p_rec["n_hits"].astype(np.int64)
+        assert (extra >= 0).all() and (extra == 1).sum() > 2000 and (extra > 1).sum() > 2000
+
+
+@pytest.mark.parametrize("mode", ["LINE", "PER_POSITION", "DIRECTION"])
+def test_posthoc_fluxmap_bit_exact(ctx, oracle, altb, mode):
+    """brdf_kind 3 through the map stage: the 45x20 / 10 cm map of nonLambertianFlux.C:307-387 (fresh rays per position),
+    the same as one LINE map, and a DIRECTION map (all through the record path), ragged batches."""
+    kw = dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000, count_all_status=1,
+              brdf_kind=3, brdf_param=(0.3, 0.4, 0.6, 0.0))
+    rpp = 40
+    n = 45 * 20 * rpp if mode == "PER_POSITION" else 30_011
+    gm = altb.map_spec(45, 20, 100.0, 10.0, getattr(altb, "MAP_" + mode), rays_per_position=rpp)
+    om = oracle.map_spec(45, 20, 100.0, 10.0, getattr(oracle, "MAP_" + mode), rays_per_position=rpp)
+    ctx.set_batch(7_001)
+    try:
+        g_counts, g_st = ctx.trace_fluxmap(altb.scene(**kw), altb.source((-60, 0, -80)), n, gm, seed=9)
+    finally:
+        ctx.set_batch(0)
+    o_counts, o_st = oracle.fluxmap(oracle.scene(**kw), oracle.source((-60, 0, -80)), n, om, seed=9, prec=oracle.F32)
+    assert np.array_equal(g_counts[0], o_counts) and o_counts.sum() > 0
+    for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
+        assert g_st[0][key] == o_st[key], key
+    with pytest.raises(Exception):
+        ctx.trace_paths(altb.scene(**kw), altb.source((-60, 0, -80)), 4, 16)
 
 
 def test_ray_id_offsets_compose(ctx, altb):
