@@ -134,6 +134,7 @@ def load_library():
     L.altb_draws_lobe.argtypes = [vp, u64, u64, u64, u32, C.c_int, C.c_double, vp]
     L.altb_trace_paths.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, u32, vp, vp, vp]
     L.altb_measure_fp32_peak.argtypes = [vp, P(C.c_double)]
+    L.altb_count_horizon.argtypes = [vp, P(Scene), P(Source), u64, u64, u64, P(u64), P(u64), P(u64)]
     _lib = L
     return L
 
@@ -288,6 +289,13 @@ class Context:
         v = C.c_double()
         self._check(self._L.altb_measure_fp32_peak(self._h, C.byref(v)))
         return v.value
+
+    def count_horizon(self, sc, src, n_rays, seed=4357, ray_id0=0):
+        """(hits whose roughness-tilted normal no longer faces the incoming ray, rays with at least one, all hits)."""
+        e, r, h = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.altb_count_horizon(self._h, C.byref(sc), C.byref(src), ray_id0, n_rays, seed,
+                                               C.byref(e), C.byref(r), C.byref(h)))
+        return e.value, r.value, h.value
 
     def trace_paths(self, sc, src, n_rays, max_points, seed=4357, ray_id0=0):
         """Polylines for small N: (points[n, max_points, 3] f32, n_points[n], status[n])."""

@@ -1216,6 +1216,39 @@ extern "C" int altb_probe_f32(altb_ctx* ctx, int op, const float* x, uint64_t n,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------- tilted normals past the horizon
+extern "C" int altb_count_horizon(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                                  uint64_t n_rays, uint64_t seed, uint64_t* n_events, uint64_t* n_rays_flagged, uint64_t* n_hits) {
+    if (!ctx || !scene || !src) return fail(ALTB_E_ARG, "altb_count_horizon: NULL argument");
+    DevCtx& d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    TraceSetup ts;
+    if (int rc = setup_trace(scene, src, seed, ts)) return rc;
+    if (ts.rescatter) return fail(ALTB_E_SCENE, "altb_count_horizon: not defined for brdf_kind 3");
+    unsigned long long h[3] = {0, 0, 0};
+    if (ts.rough && n_rays) {                       // no roughness: no tilt, nothing to count but the hits (left at 0)
+        CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
+        ts.P.sincos = d.sincos;
+        for (uint64_t off = 0, n = 0; off < n_rays; off += n) {
+            n = piece_len(ray_id0 + off, n_rays - off, 1ull << 30);
+            ts.P.ray_id0 = ray_id0 + off; ts.P.n = (uint32_t)n;
+            const unsigned blocks = (unsigned)((n + 127) / 128);
+            if (ts.model == 0) k_horizon_count<0><<<blocks, 128, 0, d.stream>>>(ts.P, d.stats);
+            else if (ts.model == 1) k_horizon_count<1><<<blocks, 128, 0, d.stream>>>(ts.P, d.stats);
+            else if (ts.model == 2) k_horizon_count<2><<<blocks, 128, 0, d.stream>>>(ts.P, d.stats);
+            else k_horizon_count<3><<<blocks, 128, 0, d.stream>>>(ts.P, d.stats);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(h, d.stats, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    if (n_events) *n_events = h[0];
+    if (n_rays_flagged) *n_rays_flagged = h[1];
+    if (n_hits) *n_hits = h[2];
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------- FP32 peak probe
 extern "C" int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return fail(ALTB_E_ARG, "altb_measure_fp32_peak: NULL argument");

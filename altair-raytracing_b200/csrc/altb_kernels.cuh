@@ -748,6 +748,52 @@ __global__ void __launch_bounds__(256) k_stats(const altb_record* __restrict__ r
     flush_stats(acc, stats);
 }
 
+// ------------------------------------------------------------------------------------ K1h horizon diagnostic
+// SURVEY.md A.3 step 2 (the reference's fluxAtObserver.C:156 / nonLambertianFlux.C:222 run with a Gaussian roughness of 0.5 rad):
+// a tilted normal may no longer face the incoming ray; ROBAST does not re-draw, neither does this library (the new direction
+// is mirrored about the TRUE tangent plane when it points into the wall).  This kernel COUNTS those events, separately from the
+// trace: out[0] += surface hits (not absorbed) with incoming . n_tilted >= 0, out[1] += rays with at least one such hit,
+// out[2] += surface hits.  Same rays, same draws as k_trace (one thread per ray, generic step, exact contract).
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_horizon_count(const __grid_constant__ TraceParams P, unsigned long long* __restrict__ out) {
+    constexpr bool NEED_G = true;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ev = 0, hits = 0;
+    if (i < P.n) {
+        const DrawTabs T = make_tabs(P.sincos);
+        RayState s;
+        s.pos = {P.x0f[0], P.x0f[1], P.x0f[2]}; s.dir = {P.d0f[0], P.d0f[1], P.d0f[2]};
+        s.hits = 0; s.where = P.kind0;
+        int st = P.kind0 == EV_EXIT ? ALTB_EXITED : 0;
+        const uint64_t rid = P.ray_id0 + i;
+        while (!st) {
+            HitDraws dr;
+            hit_from_philox<NEED_G>(P.keys, T, P.k.abs_thr, P.k.spec_thr, (uint32_t)rid, (uint32_t)(rid >> 32), s.hits, dr);
+            if (MODEL == 3) dr.u_r = lobe_accept(P.keys, rid, s.hits, P.k.lobe_n, P.k.lobe_ang);
+            if (!dr.absorb) {
+                f3 nrm, nt;
+                if (s.where == EV_WALL) nrm = scale3(P.k.neg_inv_r1, s.pos);
+                else {
+                    const double q[3] = {(double)s.pos.x, (double)s.pos.y, (double)s.pos.z};
+                    double nn[3];
+                    edge_normal(P.g, q, nn);
+                    nrm = {(float)nn[0], (float)nn[1], (float)nn[2]};
+                }
+                tilt_normal<CONTRACT_EXACT>(nrm, dr.sc_psi, dr.g0, P.k.sigma, P.k.tilt_small, nt);
+                ev += dot3(s.dir, nt) >= 0.0f;
+            }
+            st = bounce_step<true, MODEL, false>(P.g, P.k, P.k.zc, s, dr);
+        }
+        hits = s.hits;
+    }
+    const unsigned long long e = warp_sum(ev), r = warp_sum(ev ? 1ull : 0ull), h = warp_sum(hits);
+    if ((threadIdx.x & 31) == 0) {
+        if (e) atomicAdd(out, e);
+        if (r) atomicAdd(out + 1, r);
+        if (h) atomicAdd(out + 2, h);
+    }
+}
+
 // ------------------------------------------------------------------------------------ K1p post-hoc re-scatter
 // brdf_kind 3 -- the committed macro literally (nonLambertianFlux.C:246-268): the records of a plain Lambertian trace come in;
 // every ray that EXITED is re-scattered ONCE where it ended (on the world box) with the spec/diffuse mixture of

@@ -189,6 +189,15 @@ int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, uint64_t n, 
  * 3/4: sin/cos of 2 pi q / 2^20 from the azimuth table, q = (uint32) x[i]. */
 int altb_probe_f32(altb_ctx* ctx, int op, const float* x, uint64_t n, float* y);
 
+/* Diagnostic for large Gaussian roughness (fluxAtObserver.C:156, nonLambertianFlux.C:222: SetGaussianRoughness(0.5)): at how
+ * many surface hits does the roughness-tilted normal no longer face the incoming ray (incoming . n_tilted >= 0)?  ROBAST does
+ * not re-draw there and neither does this library (a new direction that points into the wall is mirrored about the true
+ * tangent plane); SURVEY.md A.3 asks for these rays to be counted separately.  Traces the same rays with the same draws as
+ * altb_trace_records: *n_events = such hits, *n_rays_flagged = rays with at least one, *n_hits = all surface hits of the
+ * rays (0 when the scene has no roughness: nothing is traced).  Any output may be NULL.  Not defined for brdf_kind 3. */
+int altb_count_horizon(altb_ctx* ctx, const altb_scene* scene, const altb_source* src, uint64_t ray_id0,
+                       uint64_t n_rays, uint64_t seed, uint64_t* n_events, uint64_t* n_rays_flagged, uint64_t* n_hits);
+
 /* FP32 FFMA-chain throughput of device 0 [TFLOP/s] (roofline denominator measured on the box). */
 int altb_measure_fp32_peak(altb_ctx* ctx, double* tflops);
 

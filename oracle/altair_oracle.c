@@ -580,6 +580,54 @@ int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, 
     return 0;
 }
 
+/* mirror of altb_count_horizon (hits whose tilted normal no longer faces the incoming ray) */
+int orc_count_horizon(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed, int prec,
+                      uint64_t* n_events, uint64_t* n_rays_flagged, uint64_t* n_hits) {
+    geom g; consts_f kf; consts_d kd;
+    if (make_geom(sc, &g, &kf, &kd)) return -1;
+    if (g.brdf_kind == 3) return -1;
+    double d0[3], x0[3];
+    int kind0 = launch(&g, src->pos, src->dir, d0, x0);
+    if (kind0 < 0) return -2;
+    uint64_t ev = 0, fl = 0, hh = 0;
+    if (sc->roughness_rad != 0.0) {
+        #pragma omp parallel for schedule(dynamic, 256) reduction(+ : ev, fl, hh)
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            float dr[ORC_DRAWS_PER_HIT];
+            uint64_t e = 0;
+            uint32_t k = 0, hits;
+            if (prec == ORC_F32) {
+                state_f s;
+                int st = start_f(&g, &kf, &s, kind0, x0, d0);
+                while (!st) {
+                    if (g.brdf_kind == 2) orc_draws_lobe(seed, ray_id0 + (uint64_t)i, k, g.lobe_n, kf.lobe_ang, dr);
+                    else orc_draws(seed, ray_id0 + (uint64_t)i, k, dr);
+                    k++;
+                    if (!(kf.rho < dr[0])) e += (uint64_t)past_horizon_f(&kf, &s, dr);
+                    st = bounce_f(&g, &kf, &s, dr);
+                }
+                hits = s.n_hits;
+            } else {
+                state_d s;
+                int st = start_d(&g, &kd, &s, kind0, x0, d0);
+                while (!st) {
+                    if (g.brdf_kind == 2) orc_draws_lobe(seed, ray_id0 + (uint64_t)i, k, g.lobe_n, kf.lobe_ang, dr);
+                    else orc_draws(seed, ray_id0 + (uint64_t)i, k, dr);
+                    k++;
+                    if (!(kd.rho < (double)dr[0])) e += (uint64_t)past_horizon_d(&kd, &s, dr);
+                    st = bounce_d(&g, &kd, &s, dr);
+                }
+                hits = s.n_hits;
+            }
+            ev += e; fl += e != 0; hh += hits;
+        }
+    }
+    if (n_events) *n_events = ev;
+    if (n_rays_flagged) *n_rays_flagged = fl;
+    if (n_hits) *n_hits = hh;
+    return 0;
+}
+
 int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,
                uint64_t n, int prec, orc_record* rec) {
     return orc_replay_ex(sc, ray0, tape, tape_off, n, prec, 0u, rec);

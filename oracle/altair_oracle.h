@@ -114,6 +114,11 @@ int orc_trace(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint
 int orc_trace_f64(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed,
                   double* pos, double* dir, uint32_t* n_hits, uint8_t* status, int n_threads);
 
+/* SURVEY.md A.3 step 2, large roughness (fluxAtObserver.C:156): surface hits (not absorbed) at which the roughness-tilted
+ * normal no longer faces the incoming ray, rays with at least one such hit, all surface hits of the rays. */
+int orc_count_horizon(const orc_scene* sc, const orc_source* src, uint64_t ray_id0, uint64_t n, uint64_t seed, int prec,
+                      uint64_t* n_events, uint64_t* n_rays_flagged, uint64_t* n_hits);
+
 /* Replay: ray i starts at ray0[i] = (pos, dir) and consumes tape records
  * tape[8*tape_off[i] .. 8*tape_off[i+1]).  Status ORC_TAPE_END if the tape runs out. */
 int orc_replay(const orc_scene* sc, const double* ray0, const float* tape, const uint64_t* tape_off,

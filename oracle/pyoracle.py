@@ -123,6 +123,8 @@ def lib():
     L.orc_sweep_pose.argtypes = [C.c_double, C.c_double, C.c_double, P(C.c_double), P(C.c_double)]
     L.orc_trace_paths.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_port_flag.argtypes = [P(Scene), C.c_void_p]
+    L.orc_count_horizon.argtypes = [P(Scene), P(Source), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                    P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
     L.orc_num_threads.restype = C.c_int
     _lib = L
     return L
@@ -231,6 +233,13 @@ def disk_hits(sc, rec, centers, rots, det_r=5.0, det_halfthick=0.1):
     if rc:
         raise RuntimeError(f"orc_disk_hits rc={rc}")
     return hits
+
+
+def count_horizon(sc, src, n, seed=4357, ray_id0=0, prec=F32):
+    e, r, h = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib().orc_count_horizon(C.byref(sc), C.byref(src), ray_id0, n, seed, prec, C.byref(e), C.byref(r), C.byref(h))
+    assert rc == 0, rc
+    return e.value, r.value, h.value
 
 
 def trace_paths(sc, src, n, max_points, seed=4357, ray_id0=0):

@@ -158,6 +158,22 @@ def test_posthoc_fluxmap_bit_exact(ctx, oracle, altb, mode):
         ctx.trace_paths(altb.scene(**kw), altb.source((-60, 0, -80)), 4, 16)
 
 
+@pytest.mark.parametrize("kw", [dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000),   # fluxAtObserver.C:147-160
+                                dict(theta_max=170.0), dict(theta_max=164.0, roughness=0.2, brdf_kind=1),
+                                dict(theta_max=170.0, lambertian=0, roughness=0.3, max_bounces=500),
+                                dict(theta_max=170.0, roughness=0.0)])
+def test_horizon_count_bit_exact(ctx, oracle, altb, kw):
+    """surface hits whose roughness-tilted normal no longer faces the incoming ray, counted separately."""
+    n = 60_000
+    got = ctx.count_horizon(altb.scene(**kw), altb.source((-60, 0, -80), (5, 2, 0)), n, seed=SEED, ray_id0=17)
+    want = oracle.count_horizon(oracle.scene(**kw), oracle.source((-60, 0, -80), (5, 2, 0)), n, seed=SEED, ray_id0=17, prec=oracle.F32)
+    assert got == want, (got, want)
+    if kw.get("roughness", 0.01) >= 0.2:
+        assert got[0] > 1000 and got[1] > 1000
+    if kw.get("roughness", 0.01) == 0.0:
+        assert got == (0, 0, 0)
+
+
 def test_ray_id_offsets_compose(ctx, altb):
     sc, src = altb.scene(), altb.source()
     full, _ = ctx.trace_records(sc, src, 50_000, seed=SEED, ray_id0=123)

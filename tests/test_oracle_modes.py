@@ -145,3 +145,22 @@ def test_detector_pose_is_the_references_misoriented_normal(oracle):
     assert oracle.lib().orc_detector_hit(p, n, 40.0, L, v) == 1
     L2 = (C.c_double * 3)(0.0, 71.1, 0.0)
     assert oracle.lib().orc_detector_hit(p, n, 40.0, L2, v) == 0
+
+
+def test_horizon_count_scales_with_roughness(oracle):
+    """hits whose roughness-tilted normal no longer faces the incoming ray.  A tilt of g sigma passes the
+    horizon when the incidence angle is within it of grazing; for Lambertian arrivals on a sphere P(cos < x) = x^2, so the
+    fraction of hits grows like E[min(1, (g sigma)^2)] / 2 for small sigma: 4e-5 at the reference's 0.01 rad, ~8 % at the
+    0.5 rad of fluxAtObserver.C:156."""
+    src = oracle.source((-60, 0, -80), (5, 2, 0))
+    frac = {}
+    for sig in (0.0, 0.01, 0.1, 0.5):
+        kw = dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=sig, max_bounces=10000)
+        e, r, h = oracle.count_horizon(oracle.scene(**kw), src, 20_000, prec=oracle.F64)
+        e32, r32, h32 = oracle.count_horizon(oracle.scene(**kw), src, 20_000, prec=oracle.F32)
+        assert abs(e - e32) <= max(3, 1e-3 * e) and abs(h - h32) <= 1e-3 * max(h, 1)
+        assert r <= e and r <= 20_000
+        frac[sig] = e / h if h else 0.0
+    assert frac[0.0] == 0.0
+    assert 1e-5 < frac[0.01] < 1e-4 and 2e-3 < frac[0.1] < 6e-3 and 0.06 < frac[0.5] < 0.11, frac
+    assert abs(frac[0.1] / frac[0.01] / 100.0 - 1) < 0.35          # ~ sigma^2
