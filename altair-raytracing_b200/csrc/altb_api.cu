@@ -507,13 +507,14 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
         M.rs = d.map_M.rs; M.pz = d.map_M.pz; M.st = d.map_M.st; M.ct = d.map_M.ct; M.cp = d.map_M.cp; M.sp = d.map_M.sp;
         M.tiles = d.map_M.tiles; M.supers = d.map_M.supers;
         M.row4 = d.map_M.row4; M.col2 = d.map_M.col2; M.det_R = d.map_M.det_R; M.det_Wr = d.map_M.det_Wr;
+        M.rc2 = d.map_M.rc2; M.RR = d.map_M.RR; M.n2R = d.map_M.n2R; M.p2R = d.map_M.p2R;
         ms.n_tiles = d.map_n_tiles; ms.line_smem = d.map_line_smem; ms.rect_smem = d.map_rect_smem;
         return 0;
     }
     if (d.map_cached) { CK(cudaDeviceSynchronize()); d.map_cached = false; }     // kernels of an earlier call may still read the old tables
     // per-row / per-column tables (Detector::setPosition, fluxAtObserverFast.C:61-80), rounded once to f32
     std::vector<float>& tab = d.tab_host;
-    tab.assign((size_t)4 * nt + 2 * np, 0.f);
+    tab.assign((size_t)5 * nt + 2 * np, 0.f);        // rs, pz, st, ct [nt each], cp, sp [np each], R ct^2 [nt]
     std::vector<double> px((size_t)nt * np), py((size_t)nt * np), pzv((size_t)nt * np);
     for (int i = 0; i < nt; i++) {
         const double th = (i + 0.5) * 90.0 / nt * PI_D / 180.0;
@@ -521,6 +522,7 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
         tab[nt + i] = (float)(-100.0 - map->det_radius * cos(th));  // pz
         tab[2 * nt + i] = (float)sin(th);                       // st
         tab[3 * nt + i] = (float)cos(th);                       // ct
+        tab[4 * nt + 2 * np + i] = (float)(map->det_radius * cos(th) * cos(th));   // R ct^2: the row part of (L - p).n (line_hit)
     }
     for (int j = 0; j < np; j++) {
         const double ph = (j + 0.5) * 360.0 / np * PI_D / 180.0;
@@ -587,23 +589,31 @@ static int setup_map(altb_ctx* ctx, DevCtx& d, const altb_scene* sc, const Geom&
         for (int b = 0; b < nsp; b++)
             best_tiles.push_back(bound(a * SUPER * bt, std::min(nt, (a + 1) * SUPER * bt), b * SUPER * bp, std::min(np, (b + 1) * SUPER * bp)));
     ms.line_smem = (size_t)LINE_BATCH * 2 * sizeof(float4) + (size_t)ms.n_tiles * LINE_WORDS * sizeof(uint32_t) +
-                   (size_t)(ms.n_tiles + nst * nsp) * sizeof(float4) + (size_t)nst * nsp * sizeof(uint32_t) + ((size_t)4 * nt + 2 * np) * sizeof(float);
+                   (size_t)(ms.n_tiles + nst * nsp) * sizeof(float4) + (size_t)nst * nsp * sizeof(uint32_t) + ((size_t)3 * nt + 2 * np) * sizeof(float);
     if (ms.line_smem > 200 * 1024) return fail(ALTB_E_ARG, "map: %d x %d bins need %zu B of shared memory", nt, np, ms.line_smem);
-    // packed copies for the ray-stationary kernel: (rs, pz, st, ct) per row, (cp, sp) per column, 16-byte aligned behind the flat tables
-    const size_t flat = ((size_t)4 * nt + 2 * np + 3) & ~(size_t)3;
+    // packed copies for the ray-stationary kernel: (st, ct, R ct^2, 0) per row, (cp, sp) per column, 16-byte aligned behind the flat tables
+    const size_t flat = ((size_t)5 * nt + 2 * np + 3) & ~(size_t)3;
     tab.resize(flat + (size_t)4 * nt + 2 * np);
-    for (int i = 0; i < nt; i++) for (int c = 0; c < 4; c++) tab[flat + 4 * i + c] = tab[(size_t)c * nt + i];
+    for (int i = 0; i < nt; i++) {
+        tab[flat + 4 * i] = tab[2 * nt + i]; tab[flat + 4 * i + 1] = tab[3 * nt + i]; tab[flat + 4 * i + 2] = tab[4 * nt + 2 * np + i];
+        tab[flat + 4 * i + 3] = 0.f;
+    }
     for (int j = 0; j < np; j++) { tab[flat + 4 * nt + 2 * j] = tab[4 * nt + j]; tab[flat + 4 * nt + 2 * j + 1] = tab[4 * nt + np + j]; }
     if (int rc = ensure(d.tables, d.tables_cap, (uint64_t)tab.size())) return rc;
     if (int rc = ensure(d.tiles, d.tiles_cap, (uint64_t)best_tiles.size())) return rc;
     CK(cudaMemcpyAsync(d.tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d.tiles, best_tiles.data(), best_tiles.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     M.rs = d.tables; M.pz = d.tables + nt; M.st = d.tables + 2 * nt; M.ct = d.tables + 3 * nt;
-    M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np;
+    M.cp = d.tables + 4 * nt; M.sp = d.tables + 4 * nt + np; M.rc2 = d.tables + 4 * nt + 2 * np;
+    M.RR = (float)(map->det_radius * map->det_radius); M.n2R = (float)(-2.0 * map->det_radius); M.p2R = (float)(2.0 * map->det_radius);
     M.tiles = d.tiles; M.supers = d.tiles + ms.n_tiles;
     M.row4 = reinterpret_cast<const float4*>(d.tables + flat); M.col2 = reinterpret_cast<const float2*>(d.tables + flat + 4 * nt);
     M.det_R = (float)map->det_radius; M.det_Wr = (float)(hw + 0.05);      // f32 evaluation of the test moves the rim by < 1e-3 cm
-    ms.rect_smem = (size_t)nt * np * sizeof(unsigned int) + (size_t)(nt + 1) * sizeof(float4) + (size_t)2 * np * sizeof(float2);
+    {
+        const size_t nrp = ((size_t)nt + 1) / 2;
+        ms.rect_smem = nrp * (sizeof(float4) + sizeof(float2)) + (size_t)RECT_THREADS * sizeof(float4) + (size_t)2 * np * sizeof(float2) +
+                       2 * nrp * (size_t)rect_hist_stride(np) * sizeof(unsigned int);
+    }
     d.map_key = *map; d.map_M = M; d.map_n_tiles = ms.n_tiles; d.map_line_smem = ms.line_smem; d.map_rect_smem = ms.rect_smem; d.map_cached = true;
     return 0;
 }

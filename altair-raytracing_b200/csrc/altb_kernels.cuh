@@ -696,8 +696,10 @@ struct MapParams {
     const double* dir_tab;         // DIRECTION mode: bin edges (direction_bin)
     int force_tiles;               // LINE modes: every ray to the tile kernel (ALTB_LINE_TILES=1, A/B measurements)
     float det_R, det_Wr;           // LINE modes: detector-hemisphere radius; det_width / 2 + 0.05 cm of f32 slack (k_prepare_lines)
-    const float4* row4;            // LINE modes: (rs, pz, st, ct) per theta row, packed for one 128-bit load
+    const float4* row4;            // LINE modes: (st, ct, R ct^2, 0) per theta row, packed for one 128-bit load
     const float2* col2;            // LINE modes: (cp, sp) per phi column
+    const float* rc2;              // [n_theta]: R cos^2(theta) (the row part of num, see line_hit)
+    float RR, n2R, p2R;            // det_radius^2, -2 det_radius, +2 det_radius
     int rays_per_position;         // per-position / twofold modes: consecutive ray ids sharing one detector position
 };
 
@@ -922,20 +924,42 @@ __global__ void __launch_bounds__(DIR_THREADS) k_map_direction(const altb_record
 }
 
 // ------------------------------------------------------------------------------------ K2b line map
-// Detector::setPosition + checkIntersection (fluxAtObserverFast.C:61-119) in the division-free f32
-// form of the arithmetic contract: hit <=> |dot*(L-p) - num*v|^2 <= w^2 * dot^2.
-__device__ __forceinline__ bool line_hit(float rs, float pz, float st, float ct, float cp, float sp, float w2,
-                                         const f3& L, const f3& v) {
-    const float p0 = rs * cp, p1 = rs * sp, p2 = pz;
-    const float n0 = -(st * sp), n1 = st * cp, n2 = -ct;
-    const float dot = fma_(v.x, n0, fma_(v.y, n1, v.z * n2));
-    const float d0 = L.x - p0, d1 = L.y - p1, d2 = L.z - p2;
-    const float num = fma_(d0, n0, fma_(d1, n1, d2 * n2));
-    const float q0 = fma_(dot, d0, -(num * v.x));
-    const float q1 = fma_(dot, d1, -(num * v.y));
-    const float q2 = fma_(dot, d2, -(num * v.z));
-    const float r2 = fma_(q0, q0, fma_(q1, q1, q2 * q2));
-    return (fabsf(dot) >= 1e-10f) && (r2 <= w2 * (dot * dot));
+// Detector::setPosition + checkIntersection (fluxAtObserverFast.C:61-119) in the f32 form of the arithmetic contract:
+// multiplied through by dot^2 (no division) and EXPANDED about the hemisphere centre c0 = (0, 0, -100).  With
+// u = (st cp, st sp, -ct) the detector centre is c0 + R u and the reference's normal (-d_y, d_x, d_z)/|d| is
+// n = (-st sp, st cp, -ct): u.n = ct^2 depends on the row only and every scalar product splits into a per-column part
+// (A, B, Cq, E: 8 operations per (ray, column)) and a per-row part (g, k, h: 3 per (ray, row)), leaving 13 operations per
+// (ray, position) test instead of 24 for the vector form |dot (L - p) - num v|^2.  The line is represented by its foot point m
+// relative to c0 (the point of the line closest to c0: |D|^2 stays ~1e4 cm^2, which bounds the cancellation of the expanded
+// form) and its direction v:   hit  <=>  dot^2 |D|^2 - 2 dot num (D.v) + num^2 |v|^2  <=  w^2 dot^2,   D = m - R u.
+// Against the literal double-precision formula 4e-6 of the hits differ (rim of the disk); the CPU checker's single-precision
+// mode restates exactly this sequence.
+struct LineC { f3 m, v; float vv, mv2, mm; };
+__device__ __forceinline__ f3 line_foot(const f3& L, const f3& v) {           // foot point relative to c0
+    const f3 Lp = {L.x, L.y, L.z + 100.0f};
+    const float t0 = -dot3(Lp, v);
+    return {fma_(t0, v.x, Lp.x), fma_(t0, v.y, Lp.y), fma_(t0, v.z, Lp.z)};
+}
+__device__ __forceinline__ LineC line_consts(const f3& m, const f3& v, float RR) {
+    LineC c;
+    c.m = m; c.v = v;
+    c.vv = dot3(v, v);
+    c.mv2 = -2.0f * dot3(m, v);
+    c.mm = fma_(m.x, m.x, fma_(m.y, m.y, fma_(m.z, m.z, RR)));
+    return c;
+}
+// per-(ray, column) terms: (A, B, Cq, E)
+__device__ __forceinline__ float4 line_col_terms(const f3& m, const f3& v, float cp, float sp) {
+    return make_float4(fma_(m.x, cp, m.y * sp), fma_(m.y, cp, -(m.x * sp)), fma_(v.x, cp, v.y * sp), fma_(v.y, cp, -(v.x * sp)));
+}
+__device__ __forceinline__ bool line_hit(const LineC& c, float st, float ct, float rc2, float cp, float sp, float n2R, float p2R, float w2) {
+    const float4 t = line_col_terms(c.m, c.v, cp, sp);
+    const float g = c.v.z * ct, k = c.m.z * ct, h = k + rc2;
+    const float dot = fma_(st, t.w, -g), num = fma_(st, t.y, -h), um = fma_(st, t.x, -k);
+    const float DD = fma_(n2R, um, c.mm), uv = fma_(st, t.z, -g), Dv2 = fma_(p2R, uv, c.mv2);
+    const float a = dot * dot, b = dot * num, cc = num * num;
+    const float r2 = fma_(a, DD, fma_(b, Dv2, cc * c.vv));
+    return (fabsf(dot) >= 1e-10f) && (r2 <= w2 * a);
 }
 
 #ifndef ALTB_LINE_BATCH
@@ -950,8 +974,8 @@ static constexpr int LINE_THREADS = ALTB_LINE_THREADS;
 static constexpr int SUPER = 4;             // a super-tile is SUPER x SUPER tiles
 
 // dynamic shared memory layout:
-//   float4 rays[LINE_BATCH][2]; uint32 bitmap[n_tiles][LINE_WORDS]; float4 tiles[n_tiles]; float4 supers[n_super];
-//   uint32 sup_ij[n_super]; tables
+//   float4 rays[LINE_BATCH][2] (m.xyz, v.x | v.yz, |v|^2, -2 m.v); uint32 bitmap[n_tiles][LINE_WORDS]; float4 tiles[n_tiles];
+//   float4 supers[n_super]; uint32 sup_ij[n_super]; tables (st, ct, R ct^2 per row; cp, sp per column)
 // (its list grows from the BACK of the line buffer: entry e = lines_end[-2 (e + 1)], lines_end[-2 (e + 1) + 1])
 __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restrict__ lines_end,
                                                            const unsigned int* __restrict__ n_lines_ptr, const MapParams M,
@@ -965,13 +989,13 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
     float4* s_tiles = reinterpret_cast<float4*>(bitmap + (size_t)n_tiles * LINE_WORDS);
     float4* s_super = s_tiles + n_tiles;
     uint32_t* s_sup_ij = reinterpret_cast<uint32_t*>(s_super + n_super);          // first tile (ti << 16 | tj) of each super-tile
-    float* t_rs = reinterpret_cast<float*>(s_sup_ij + n_super);
-    float* t_pz = t_rs + M.n_theta; float* t_st = t_pz + M.n_theta; float* t_ct = t_st + M.n_theta;
+    float* t_rc = reinterpret_cast<float*>(s_sup_ij + n_super);
+    float* t_st = t_rc + M.n_theta; float* t_ct = t_st + M.n_theta;
     float* t_cp = t_ct + M.n_theta; float* t_sp = t_cp + M.n_phi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = LINE_THREADS / 32;
 
-    for (int i = tid; i < M.n_theta; i += LINE_THREADS) { t_rs[i] = M.rs[i]; t_pz[i] = M.pz[i]; t_st[i] = M.st[i]; t_ct[i] = M.ct[i]; }
+    for (int i = tid; i < M.n_theta; i += LINE_THREADS) { t_rc[i] = M.rc2[i]; t_st[i] = M.st[i]; t_ct[i] = M.ct[i]; }
     for (int j = tid; j < M.n_phi; j += LINE_THREADS) { t_cp[j] = M.cp[j]; t_sp[j] = M.sp[j]; }
     for (int t = tid; t < n_tiles; t += LINE_THREADS) s_tiles[t] = M.tiles[t];
     for (int t = tid; t < n_super; t += LINE_THREADS) {
@@ -986,13 +1010,18 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
         const int nwords = (nr + 31) >> 5;
         __syncthreads();                                 // previous pass is done with rays / bitmap
         for (int w = tid; w < n_tiles * LINE_WORDS; w += LINE_THREADS) bitmap[w] = 0u;
-        for (int k = tid; k < 2 * nr; k += LINE_THREADS) rays[k] = __ldg(lines_end - 2 * (ptrdiff_t)(cur + (k >> 1) + 1) + (k & 1));
+        for (int k = tid; k < nr; k += LINE_THREADS) {       // the list holds (m.xyz, v.x | v.yz, -, -): add the ray's |v|^2 and -2 m.v
+            const float4 a = __ldg(lines_end - 2 * (ptrdiff_t)(cur + k + 1)), b = __ldg(lines_end - 2 * (ptrdiff_t)(cur + k + 1) + 1);
+            const f3 m = {a.x, a.y, a.z}, v = {a.w, b.x, b.y};
+            rays[2 * k] = a;
+            rays[2 * k + 1] = make_float4(b.x, b.y, dot3(v, v), -2.0f * dot3(m, v));
+        }
         __syncthreads();
         // ---- phase 1: conservative two-level culling, one ray per warp pass, lanes = (super-)tiles.
         //      dist(centre, line)^2 <= (w + r + slack)^2 is necessary for any bin of the (super-)tile to be hit.
         for (int r = warp; r < nr; r += NW) {
             const float4 ra = rays[2 * r], rb = rays[2 * r + 1];
-            const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
+            const f3 L = {ra.x, ra.y, ra.z - 100.0f}, v = {ra.w, rb.x, rb.y};       // a point of the line in scene coordinates
             const uint32_t rbit = 1u << (r & 31);
             const int rword = r >> 5;
             for (int s0 = 0; s0 < n_super; s0 += 32) {
@@ -1036,7 +1065,7 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
             while (tj >= M.nt_phi) { tj -= M.nt_phi; ti++; }
             const bool inb = (lane < M.t_theta * M.t_phi) && i < M.n_theta && j < M.n_phi;
             const int ii = inb ? i : 0, jj = inb ? j : 0;
-            const float rs = t_rs[ii], pz = t_pz[ii], st = t_st[ii], ct = t_ct[ii], cp = t_cp[jj], sp = t_sp[jj];
+            const float rc = t_rc[ii], st = t_st[ii], ct = t_ct[ii], cp = t_cp[jj], sp = t_sp[jj];
             unsigned int acc = 0;
             for (int w = 0; w < nwords; w++) {
                 unsigned bits = bitmap[t * LINE_WORDS + w];
@@ -1045,8 +1074,10 @@ __global__ void __launch_bounds__(LINE_THREADS) k_map_line(const float4* __restr
                     const int b = __ffs(bits) - 1;
                     bits &= bits - 1;
                     const float4 ra = base[2 * b], rb = base[2 * b + 1];
-                    const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
-                    acc += line_hit(rs, pz, st, ct, cp, sp, M.w2, L, v) ? 1u : 0u;
+                    LineC lc;
+                    lc.m = {ra.x, ra.y, ra.z}; lc.v = {ra.w, rb.x, rb.y}; lc.vv = rb.z; lc.mv2 = rb.w;
+                    lc.mm = fma_(ra.x, ra.x, fma_(ra.y, ra.y, fma_(ra.z, ra.z, M.RR)));
+                    acc += line_hit(lc, st, ct, rc, cp, sp, M.n2R, M.p2R, M.w2) ? 1u : 0u;
                 }
             }
             if (inb && acc) atomicAdd(counts + (size_t)i * M.n_phi + j, (unsigned long long)acc);
@@ -1096,7 +1127,8 @@ __device__ __forceinline__ void emit_line(const RectParams& RP, bool pf, const f
         const unsigned below = (1u << lane) - 1u;
         float4* dst = rect ? lines + 2 * (size_t)(base_r + __popc(mr & below))          // rectangle list from the front,
                            : lines + 2 * ((size_t)lines_cap - 1 - (base_t + __popc(mt & below)));   // tile list from the back
-        dst[0] = make_float4(L.x, L.y, L.z, v.x);
+        const f3 m = line_foot(L, v);           // the map kernels' representation of the line (line_hit)
+        dst[0] = make_float4(m.x, m.y, m.z, v.x);
         dst[1] = make_float4(v.y, v.z, __uint_as_float(r1), __uint_as_float(r2));
     }
 }
@@ -1133,25 +1165,19 @@ __global__ void __launch_bounds__(256) k_prepare_raw(const float4* __restrict__ 
     }
 }
 
-// line_hit of two neighbouring theta rows (a, b) of one phi column, packed: rs = (rs_a, rs_b) etc.; same operations, same
-// order, same bits as line_hit
-__device__ __forceinline__ void line_hit2(const float2 rs, const float2 pz, const float2 st, const float2 ct, const float cp, const float sp,
-                                          float w2, const f3& L, const f3& v, bool& hit_a, bool& hit_b) {
-    const float2 cp2 = make_float2(cp, cp), sp2 = make_float2(sp, sp);
-    const float2 p0 = __fmul2_rn(rs, cp2), p1 = __fmul2_rn(rs, sp2);
-    const float2 t0 = __fmul2_rn(st, sp2), n1 = __fmul2_rn(st, cp2);
-    const float2 n0 = make_float2(-t0.x, -t0.y), n2 = make_float2(-ct.x, -ct.y);
-    const float2 dot = __ffma2_rn(make_float2(v.x, v.x), n0, __ffma2_rn(make_float2(v.y, v.y), n1, __fmul2_rn(make_float2(v.z, v.z), n2)));
-    const float2 d0 = __fadd2_rn(make_float2(L.x, L.x), make_float2(-p0.x, -p0.y));
-    const float2 d1 = __fadd2_rn(make_float2(L.y, L.y), make_float2(-p1.x, -p1.y));
-    const float2 d2 = __fadd2_rn(make_float2(L.z, L.z), make_float2(-pz.x, -pz.y));
-    const float2 num = __ffma2_rn(d0, n0, __ffma2_rn(d1, n1, __fmul2_rn(d2, n2)));
-    const float2 nvx = __fmul2_rn(num, make_float2(v.x, v.x)), nvy = __fmul2_rn(num, make_float2(v.y, v.y)), nvz = __fmul2_rn(num, make_float2(v.z, v.z));
-    const float2 q0 = __ffma2_rn(dot, d0, make_float2(-nvx.x, -nvx.y));
-    const float2 q1 = __ffma2_rn(dot, d1, make_float2(-nvy.x, -nvy.y));
-    const float2 q2 = __ffma2_rn(dot, d2, make_float2(-nvz.x, -nvz.y));
-    const float2 r2 = __ffma2_rn(q0, q0, __ffma2_rn(q1, q1, __fmul2_rn(q2, q2)));
-    const float2 lim = __fmul2_rn(make_float2(w2, w2), __fmul2_rn(dot, dot));
+// line_hit of two neighbouring theta rows (a, b) of one phi column, packed over the rows: st = (st_a, st_b) etc., the column
+// terms t = (A, B, Cq, E) broadcast; same operations, same order, same bits as line_hit.  g, k, h: the row terms.
+__device__ __forceinline__ void line_hit2(const float2 st, const float2 g, const float2 k, const float2 h, const float4 t,
+                                          float vv, float mv2, float mm, float n2R, float p2R, float w2, bool& hit_a, bool& hit_b) {
+    const float2 dot = __ffma2_rn(st, make_float2(t.w, t.w), make_float2(-g.x, -g.y));
+    const float2 num = __ffma2_rn(st, make_float2(t.y, t.y), make_float2(-h.x, -h.y));
+    const float2 um = __ffma2_rn(st, make_float2(t.x, t.x), make_float2(-k.x, -k.y));
+    const float2 DD = __ffma2_rn(make_float2(n2R, n2R), um, make_float2(mm, mm));
+    const float2 uv = __ffma2_rn(st, make_float2(t.z, t.z), make_float2(-g.x, -g.y));
+    const float2 Dv2 = __ffma2_rn(make_float2(p2R, p2R), uv, make_float2(mv2, mv2));
+    const float2 a = __fmul2_rn(dot, dot), b = __fmul2_rn(dot, num), cc = __fmul2_rn(num, num);
+    const float2 r2 = __ffma2_rn(a, DD, __ffma2_rn(b, Dv2, __fmul2_rn(cc, make_float2(vv, vv))));
+    const float2 lim = __fmul2_rn(make_float2(w2, w2), a);
     hit_a = (fabsf(dot.x) >= 1e-10f) && (r2.x <= lim.x);
     hit_b = (fabsf(dot.y) >= 1e-10f) && (r2.y <= lim.y);
 }
@@ -1160,65 +1186,112 @@ __device__ __forceinline__ void line_hit2(const float2 rs, const float2 pz, cons
 #define ALTB_RECT_THREADS 1024
 #endif
 static constexpr int RECT_THREADS = ALTB_RECT_THREADS;      // one 1024-thread block per SM: 32 warps (64 registers), ONE histogram to flush
-// dynamic shared memory: float4 rowp[2 * ceil(n_theta / 2)] -- entries 2k, 2k+1 = (rs_a, rs_b, pz_a, pz_b), (st_a, st_b, ct_a, ct_b)
-// of the row pair (2k, 2k+1); float2 col[2 n_phi] (cos, sin), the table twice in a row so that a rectangle that wraps around
-// phi = 360 deg reads straight on; uint32 hist[n_bins].
+// floor(x / n) = x * RCP32[n] >> 16 for x <= 32, n = 1 .. 32 (RCP32[n] = ceil(65536 / n)): how a warp's lanes split into
+// column groups of n row pairs, without the integer-division subroutine
+__device__ __constant__ unsigned int RCP32[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682,
+                                                  4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185,
+                                                  2115, 2048};
+// k_map_line_rect, row-stationary.  A warp takes one ray at a time.  Its lanes split into G = 32 / n column groups of n row
+// pairs (n = row pairs of the rectangle, at most 32 per block of rows): lane (g, r) keeps row pair r for the whole rectangle --
+// its row terms (g, k, h: 3 packed operations) are computed once -- and walks the columns g, g + G, ...; the column terms
+// (A, B, Cq, E: 4 packed operations) are computed once per (ray, column) by one lane each and handed round through a 512-byte
+// scratch line per warp.  A pass is then ONE 128-bit shared load + 13 packed operations for two tests (it was three loads +
+// 27, with both index pairs recomputed per pass), and the index arithmetic of a pass is one add.
+// The histogram keeps the even and the odd rows in separate halves with an ODD row stride (the lanes of a pass increment
+// bins of one column in consecutive row pairs, which then fall into different banks) and has 2 n_phi columns per row, like
+// the column table: a rectangle that wraps around phi = 360 deg writes straight on, the flush folds the halves together.
+// dynamic shared memory: float4 rowp[nrp] = (st_a, st_b, ct_a, ct_b), float2 rowc[nrp] = R ct^2 (a, b) of the row pair (2k, 2k+1);
+// float2 col[2 n_phi] (cos, sin), the table twice in a row so that a rectangle that wraps around phi = 360 deg reads straight on;
+// float4 scratch[warps][32]; uint32 hist[2][nrp][stride].
+__device__ __host__ inline int rect_hist_stride(int n_phi) { return (2 * n_phi) | 1; }
 __global__ void __launch_bounds__(RECT_THREADS, 1024 / RECT_THREADS) k_map_line_rect(const float4* __restrict__ lines, const unsigned int* __restrict__ n_lines_ptr,
                                                                 const MapParams M, unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char rect_smem[];
-    const int nb = M.n_theta * M.n_phi, np = M.n_phi, nrp = (M.n_theta + 1) >> 1;
+    const int np = M.n_phi, nrp = (M.n_theta + 1) >> 1, hs = rect_hist_stride(np);
     float4* s_row = reinterpret_cast<float4*>(rect_smem);
-    float2* s_col = reinterpret_cast<float2*>(s_row + 2 * nrp);
+    float4* s_scr = s_row + nrp;
+    float2* s_rc = reinterpret_cast<float2*>(s_scr + RECT_THREADS);
+    float2* s_col = s_rc + nrp;
     unsigned int* hist = reinterpret_cast<unsigned int*>(s_col + 2 * np);
     for (int k = threadIdx.x; k < nrp; k += RECT_THREADS) {
-        const float4 a = M.row4[2 * k], b = M.row4[min(2 * k + 1, M.n_theta - 1)];     // (rs, pz, st, ct)
-        s_row[2 * k] = make_float4(a.x, b.x, a.y, b.y);
-        s_row[2 * k + 1] = make_float4(a.z, b.z, a.w, b.w);
+        const float4 a = M.row4[2 * k], b = M.row4[min(2 * k + 1, M.n_theta - 1)];     // (st, ct, R ct^2, -)
+        s_row[k] = make_float4(a.x, b.x, a.y, b.y);
+        s_rc[k] = make_float2(a.z, b.z);
     }
     for (int j = threadIdx.x; j < 2 * np; j += RECT_THREADS) s_col[j] = M.col2[j < np ? j : j - np];
-    for (int b = threadIdx.x; b < nb; b += RECT_THREADS) hist[b] = 0u;
+    for (int b = threadIdx.x; b < 2 * nrp * hs; b += RECT_THREADS) hist[b] = 0u;
     __syncthreads();
     const unsigned n_lines = *n_lines_ptr;
     const int lane = threadIdx.x & 31;
+    float4* scr = s_scr + (threadIdx.x & ~31);
+    const unsigned hb_bytes = 4u * (unsigned)(nrp * hs);     // from an even row's bin to the odd row's of the same pair
+    const float n2R = M.n2R, p2R = M.p2R, w2 = M.w2;
     const unsigned gw = (blockIdx.x * RECT_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * RECT_THREADS) >> 5;
     // one ray per warp pass (uniform loads: one transaction each); the next ray's line is in flight while this one is tested
     float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
     if (gw < n_lines) { ra = __ldg(lines + 2 * (size_t)gw); rb = __ldg(lines + 2 * (size_t)gw + 1); }
     for (unsigned r = gw; r < n_lines; r += nw) {
-        const f3 L = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
+        const f3 m = {ra.x, ra.y, ra.z}, v = {ra.w, rb.x, rb.y};
         const uint32_t rect0 = __float_as_uint(rb.z), rect1 = __float_as_uint(rb.w);
         if (r + nw < n_lines) { ra = __ldg(lines + 2 * (size_t)(r + nw)); rb = __ldg(lines + 2 * (size_t)(r + nw) + 1); }
+        const LineC lc = line_consts(m, v, M.RR);
 #pragma unroll 1
         for (int k = 0; k < 2; k++) {
             const uint32_t ru = k ? rect1 : rect0;
             if (!ru) break;
             const LineRect R = unpack_rect(ru);                     // i0 even, ni even
-            const int nj = R.nj, total = (R.ni >> 1) * nj;
-            // lane t of the pass -> (row pair ii, column jj); the next pass is 32 tests further: ii += 32 / nj, jj += 32 % nj (+ carry)
-            const int q32 = 32 / nj, r32 = 32 - q32 * nj;
-            int ii = lane / nj, jj = lane - ii * nj;
-            for (int t = lane; t < total; t += 32) {
-                const int i = R.i0 + 2 * ii, jx = R.j0 + jj;        // jx < 2 n_phi: index into the doubled column table
-                const float4 ra4 = s_row[i], rb4 = s_row[i + 1];
-                const float2 c = s_col[jx];
-                bool ha, hb;
-                line_hit2(make_float2(ra4.x, ra4.y), make_float2(ra4.z, ra4.w), make_float2(rb4.x, rb4.y), make_float2(rb4.z, rb4.w),
-                          c.x, c.y, M.w2, L, v, ha, hb);
-                hb = hb && i + 1 < M.n_theta;
-                if (ha | hb) {
-                    unsigned int* hp = hist + i * np + (jx >= np ? jx - np : jx);
-                    if (ha) atomicAdd(hp, 1u);
-                    if (hb) atomicAdd(hp + np, 1u);
+            const int npairs = R.ni >> 1, p0 = R.i0 >> 1;
+#pragma unroll 1
+            for (int pb = 0; pb < npairs; pb += 32) {               // blocks of at most 32 row pairs (one block unless the cap spans > 64 rows)
+                const int n = min(32, npairs - pb);
+                const unsigned rcp = RCP32[n];
+                const int G = (int)((32u * rcp) >> 16);             // column groups
+                const int g = (int)(((unsigned)lane * rcp) >> 16), rr = lane - g * n;
+                const bool row_ok = g < G;
+                const int pi = p0 + pb + (row_ok ? rr : 0);         // this lane's row pair
+                const float4 rw = s_row[pi];
+                const float2 st2 = make_float2(rw.x, rw.y), ct2 = make_float2(rw.z, rw.w);
+                const float2 g2 = __fmul2_rn(make_float2(v.z, v.z), ct2), k2 = __fmul2_rn(make_float2(m.z, m.z), ct2);
+                const float2 h2 = __fadd2_rn(k2, s_rc[pi]);
+                // (odd n_theta: the last pair's second row is a copy of the first; its bins are dropped by the flush)
+                unsigned int* hrow = hist + pi * hs + R.j0;         // + column of the rectangle; the odd rows' half is hb_off words on
+#pragma unroll 1
+                for (int cc = 0; cc < R.nj; cc += 32) {             // chunks of 32 columns
+                    const int ncol = min(32, R.nj - cc);
+                    __syncwarp();
+                    if (lane < ncol) {
+                        const float2 c = s_col[R.j0 + cc + lane];   // < 2 n_phi: the doubled column table
+                        scr[lane] = line_col_terms(m, v, c.x, c.y);
+                    }
+                    __syncwarp();
+                    if (row_ok) {
+                        // shared-space addresses, advanced by G columns per pass.  The increments are UNCONDITIONAL reds of 0 or 1:
+                        // a warp nearly always holds a lane that hits, so the instruction would run anyway, and around
+                        // `if (hit) atomicAdd(p, 1)` ptxas builds a branch + reconvergence pair per increment (6 instructions per pass)
+                        unsigned hp = (unsigned)__cvta_generic_to_shared(hrow + cc + g);
+                        const float4* sp = scr + g;
+                        for (int c = g; c < ncol; c += G, sp += G, hp += 4u * (unsigned)G) {
+                            bool ha, hb;
+                            line_hit2(st2, g2, k2, h2, *sp, lc.vv, lc.mv2, lc.mm, n2R, p2R, w2, ha, hb);
+                            asm volatile("red.shared.add.u32 [%0], %2;\n\tred.shared.add.u32 [%1], %3;"
+                                         :: "r"(hp), "r"(hp + hb_bytes), "r"((unsigned)ha), "r"((unsigned)hb) : "memory");
+                        }
+                    }
                 }
-                ii += q32; jj += r32;
-                if (jj >= nj) { jj -= nj; ii++; }
             }
         }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += RECT_THREADS) {
+    for (int b = threadIdx.x; b < 2 * nrp * hs; b += RECT_THREADS) {
         const unsigned int c = hist[b];
-        if (c) atomicAdd(counts + b, (unsigned long long)c);
+        if (c) {
+            const int half = b >= nrp * hs, rem = b - half * nrp * hs;
+            const int pi = rem / hs;
+            int col = rem - pi * hs;
+            if (col >= np) col -= np;
+            const int row = 2 * pi + half;
+            if (col < np && row < M.n_theta) atomicAdd(counts + (size_t)row * np + col, (unsigned long long)c);
+        }
     }
 }
 
@@ -1242,11 +1315,12 @@ __global__ void __launch_bounds__(256) k_map_per_position(const altb_record* __r
         int i, j;
         if (M.mode == ALTB_MAP_TWOFOLD) { i = (int)(g / half); j = (int)(g % half); }
         else { i = (int)(g / M.n_phi); j = (int)(g % M.n_phi); }
-        if (line_hit(M.rs[i], M.pz[i], M.st[i], M.ct[i], M.cp[j], M.sp[j], M.w2, pos, dir))
+        const LineC lc = line_consts(line_foot(pos, dir), dir, M.RR);
+        if (line_hit(lc, M.st[i], M.ct[i], M.rc2[i], M.cp[j], M.sp[j], M.n2R, M.p2R, M.w2))
             atomicAdd(counts + (size_t)i * M.n_phi + j, 1ull);
         if (M.mode == ALTB_MAP_TWOFOLD) {
             const int j2 = j + half;
-            if (line_hit(M.rs[i], M.pz[i], M.st[i], M.ct[i], M.cp[j2], M.sp[j2], M.w2, pos, dir))
+            if (line_hit(lc, M.st[i], M.ct[i], M.rc2[i], M.cp[j2], M.sp[j2], M.n2R, M.p2R, M.w2))
                 atomicAdd(counts + (size_t)i * M.n_phi + j2, 1ull);
         }
     }

@@ -723,18 +723,16 @@ int32_t orc_direction_bin(const orc_map_spec* map, const float d[3]) {
     return i * map->n_phi + j;
 }
 
-typedef struct { float* rs; float* pz; float* st; float* ct; float* cp; float* sp; float w2; } map_tab_f;
+typedef struct { float* st; float* ct; float* rc2; float* cp; float* sp; float w2, RR, n2R, p2R; } map_tab_f;
 
 static void make_tab_f(const orc_map_spec* map, map_tab_f* t) {
     int nt = map->n_theta, np = map->n_phi;
-    t->rs = malloc(sizeof(float) * nt); t->pz = malloc(sizeof(float) * nt);
-    t->st = malloc(sizeof(float) * nt); t->ct = malloc(sizeof(float) * nt);
+    t->st = malloc(sizeof(float) * nt); t->ct = malloc(sizeof(float) * nt); t->rc2 = malloc(sizeof(float) * nt);
     t->cp = malloc(sizeof(float) * np); t->sp = malloc(sizeof(float) * np);
     for (int i = 0; i < nt; i++) {
         double th = (i + 0.5) * 90.0 / nt * PI_D / 180.0;
         t->st[i] = (float)sin(th); t->ct[i] = (float)cos(th);
-        t->rs[i] = (float)(map->det_radius * sin(th));
-        t->pz[i] = (float)(-100.0 - map->det_radius * cos(th));
+        t->rc2[i] = (float)(map->det_radius * cos(th) * cos(th));
     }
     for (int j = 0; j < np; j++) {
         double ph = (j + 0.5) * 360.0 / np * PI_D / 180.0;
@@ -742,22 +740,38 @@ static void make_tab_f(const orc_map_spec* map, map_tab_f* t) {
     }
     double hw = map->det_width / 2;
     t->w2 = (float)(hw * hw);
+    t->RR = (float)(map->det_radius * map->det_radius);
+    t->n2R = (float)(-2.0 * map->det_radius); t->p2R = (float)(2.0 * map->det_radius);
 }
-static void free_tab_f(map_tab_f* t) { free(t->rs); free(t->pz); free(t->st); free(t->ct); free(t->cp); free(t->sp); }
+static void free_tab_f(map_tab_f* t) { free(t->st); free(t->ct); free(t->rc2); free(t->cp); free(t->sp); }
 
-/* the kernels' division-free f32 line-disk test (DESIGN.md "map stage") */
-static inline int line_hit_f32(const map_tab_f* t, int i, int j, const float* L, const float* v) {
-    float p0 = t->rs[i] * t->cp[j], p1 = t->rs[i] * t->sp[j], p2 = t->pz[i];
-    float n0 = -(t->st[i] * t->sp[j]), n1 = t->st[i] * t->cp[j], n2 = -t->ct[i];
-    float dot = fmaf(v[0], n0, fmaf(v[1], n1, v[2] * n2));
-    if (fabsf(dot) < 1e-10f) return 0;
-    float d0 = L[0] - p0, d1 = L[1] - p1, d2 = L[2] - p2;
-    float num = fmaf(d0, n0, fmaf(d1, n1, d2 * n2));
-    float q0 = fmaf(dot, d0, -(num * v[0]));
-    float q1 = fmaf(dot, d1, -(num * v[1]));
-    float q2 = fmaf(dot, d2, -(num * v[2]));
-    float r2 = fmaf(q0, q0, fmaf(q1, q1, q2 * q2));
-    return r2 <= t->w2 * (dot * dot);
+/* The kernels' f32 line-disk test (DESIGN.md "map stage"): Detector::setPosition + checkIntersection
+ * (fluxAtObserverFast.C:61-119) multiplied through by dot^2 and EXPANDED about the hemisphere centre c0 = (0, 0, -100).
+ * With u = (st cp, st sp, -ct) the detector centre is c0 + R u and the reference's normal (-d_y, d_x, d_z)/|d| is
+ * n = (-st sp, st cp, -ct), so that u.n = ct^2 depends on the row only and every scalar product splits into a per-column
+ * and a per-row part.  The line is represented by its foot point m (relative to c0: the point of the line closest to c0,
+ * which keeps |D|^2 small -- 1e4 instead of 1e5 cm^2 -- and with it the cancellation in the expanded form) and v:
+ *   hit  <=>  |dot D - num v|^2 = dot^2 |D|^2 - 2 dot num (D.v) + num^2 |v|^2  <=  w^2 dot^2,   D = m - R u.
+ * Against the literal double-precision formula 4e-6 of the hits differ (rim of the disk). */
+typedef struct { float m[3], v[3], vv, mv2, mm; } line_f;
+static inline void make_line_f32(const map_tab_f* t, const float* L, const float* v, line_f* c) {
+    float Lp[3] = {L[0], L[1], L[2] + 100.0f};
+    float t0 = -fmaf(Lp[0], v[0], fmaf(Lp[1], v[1], Lp[2] * v[2]));
+    for (int i = 0; i < 3; i++) { c->m[i] = fmaf(t0, v[i], Lp[i]); c->v[i] = v[i]; }
+    c->vv = fmaf(v[0], v[0], fmaf(v[1], v[1], v[2] * v[2]));
+    c->mv2 = -2.0f * fmaf(c->m[0], v[0], fmaf(c->m[1], v[1], c->m[2] * v[2]));
+    c->mm = fmaf(c->m[0], c->m[0], fmaf(c->m[1], c->m[1], fmaf(c->m[2], c->m[2], t->RR)));
+}
+static inline int line_hit_f32(const map_tab_f* t, int i, int j, const line_f* c) {
+    float cp = t->cp[j], sp = t->sp[j], st = t->st[i], ct = t->ct[i];
+    float A = fmaf(c->m[0], cp, c->m[1] * sp), B = fmaf(c->m[1], cp, -(c->m[0] * sp));
+    float Cq = fmaf(c->v[0], cp, c->v[1] * sp), E = fmaf(c->v[1], cp, -(c->v[0] * sp));
+    float g = c->v[2] * ct, k = c->m[2] * ct, h = k + t->rc2[i];
+    float dot = fmaf(st, E, -g), num = fmaf(st, B, -h), um = fmaf(st, A, -k);
+    float DD = fmaf(t->n2R, um, c->mm), uv = fmaf(st, Cq, -g), Dv2 = fmaf(t->p2R, uv, c->mv2);
+    float a = dot * dot, b = dot * num, cc = num * num;
+    float r2 = fmaf(a, DD, fmaf(b, Dv2, cc * c->vv));
+    return fabsf(dot) >= 1e-10f && r2 <= t->w2 * a;
 }
 
 int orc_map_records(const orc_scene* sc, const orc_map_spec* map, const orc_record* rec, uint64_t n,
@@ -783,7 +797,7 @@ int orc_map_records_at(const orc_scene* sc, const orc_map_spec* map, const orc_r
             int i = two ? (int)(grp / half) : (int)(grp / np), j = two ? (int)(grp % half) : (int)(grp % np);
             for (int rep = 0; rep < (two ? 2 : 1); rep++, j += half) {
                 int hit;
-                if (prec == ORC_F32) hit = line_hit_f32(&tab, i, j, rec[r].pos, rec[r].dir);
+                if (prec == ORC_F32) { line_f lc; make_line_f32(&tab, rec[r].pos, rec[r].dir, &lc); hit = line_hit_f32(&tab, i, j, &lc); }
                 else {
                     double p[3], nn[3], L[3] = {rec[r].pos[0], rec[r].pos[1], rec[r].pos[2]}, v[3] = {rec[r].dir[0], rec[r].dir[1], rec[r].dir[2]};
                     orc_detector_pose((i + 0.5) * 90.0 / nt, (j + 0.5) * 360.0 / np, map->det_radius, p, nn);
@@ -830,9 +844,11 @@ int orc_map_records_at(const orc_scene* sc, const orc_map_spec* map, const orc_r
                 } else {
                     for (int c = 0; c < 3; c++) { L[c] = rec[r].pos[c]; v[c] = rec[r].dir[c]; }
                 }
+                line_f lc;
+                make_line_f32(&tab, L, v, &lc);
                 for (int i = 0; i < nt; i++)
                     for (int j = 0; j < np; j++)
-                        loc[i * np + j] += (uint64_t)line_hit_f32(&tab, i, j, L, v);
+                        loc[i * np + j] += (uint64_t)line_hit_f32(&tab, i, j, &lc);
             } else {
                 double L[3], v[3];
                 if (compat) {
