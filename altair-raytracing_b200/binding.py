@@ -14,7 +14,7 @@ _LIB_PATH = os.environ.get("ALTB_LIB") or os.path.join(_PKG, "libaltair_b200.so"
 
 EXITED, ABSORBED, SUSPENDED, TAPE_END = 1, 2, 3, 4
 MAP_LINE, MAP_TRACEONCE_COMPAT, MAP_DIRECTION, MAP_PER_POSITION, MAP_TWOFOLD = 0, 1, 2, 3, 4
-CONTRACT_EXACT, CONTRACT_FAST = 0, 1
+CONTRACT_EXACT, CONTRACT_FAST, CONTRACT_FAST7 = 0, 1, 2
 
 RECORD_DTYPE = np.dtype([("pos", "<f4", 3), ("dir", "<f4", 3), ("n_hits", "<u4"), ("status", "<u4")])
 
@@ -191,7 +191,7 @@ class Context:
         return int(self._L.altb_trace_launch_count(self._h))
 
     def set_contract(self, contract):
-        """CONTRACT_EXACT (bit-exact vs the CPU oracle, default) or CONTRACT_FAST (special-function unit; include/altair_b200.h)."""
+        """CONTRACT_EXACT (bit-exact vs the CPU oracle, default), CONTRACT_FAST (special-function unit) or CONTRACT_FAST7 (+ Philox4x32-7); include/altair_b200.h."""
         self._check(self._L.altb_set_contract(self._h, int(contract)))
 
     @property

@@ -271,7 +271,7 @@ extern "C" int altb_set_batch(altb_ctx* ctx, uint64_t batch_rays) {
 
 extern "C" int altb_set_contract(altb_ctx* ctx, int contract) {
     if (!ctx) return fail(ALTB_E_ARG, "ctx is NULL");
-    if (contract != ALTB_CONTRACT_EXACT && contract != ALTB_CONTRACT_FAST) return fail(ALTB_E_ARG, "altb_set_contract: unknown contract %d", contract);
+    if (contract != ALTB_CONTRACT_EXACT && contract != ALTB_CONTRACT_FAST && contract != ALTB_CONTRACT_FAST7) return fail(ALTB_E_ARG, "altb_set_contract: unknown contract %d", contract);
     ctx->contract = contract;
     return 0;
 }
@@ -434,9 +434,10 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         else          { if (ts.model == 0) GEN(false, 0); else if (ts.model == 1) GEN(false, 1); else if (ts.model == 2) GEN(false, 2); else GEN(false, 3); }
 #undef GEN
     } else {
-        const bool fast = ctx->contract == ALTB_CONTRACT_FAST && ts.model <= 1;      // other models: exact instances only
-        le = fast ? launch_trace_c<CONTRACT_FAST>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
-                  : launch_trace_c<CONTRACT_EXACT>(sink, ts.rough, ts.model, P, rec, counter, blocks, st);
+        const bool fast = ctx->contract != ALTB_CONTRACT_EXACT && ts.model <= 1;      // other models: exact instances only
+        le = !fast ? launch_trace_c<CONTRACT_EXACT>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
+           : ctx->contract == ALTB_CONTRACT_FAST7 ? launch_trace_c<CONTRACT_FAST7>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
+                                                  : launch_trace_c<CONTRACT_FAST>(sink, ts.rough, ts.model, P, rec, counter, blocks, st);
     }
     ctx->launches++;
     ctx->trace_launches++;
@@ -1137,7 +1138,7 @@ extern "C" int altb_replay_ex(altb_ctx* ctx, const altb_scene* scene, const doub
         const float4* t4 = reinterpret_cast<const float4*>(d_tape);
         cudaEventRecord(d.ev[0], d.stream);
         {
-            const bool fast = ctx->contract == ALTB_CONTRACT_FAST && model <= 1, az = (flags & ALTB_REPLAY_FULL_AZIMUTH) != 0;
+            const bool fast = ctx->contract != ALTB_CONTRACT_EXACT && model <= 1, az = (flags & ALTB_REPLAY_FULL_AZIMUTH) != 0;
             if (fast) { if (az) launch_replay_c<CONTRACT_FAST, true>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
                         else launch_replay_c<CONTRACT_FAST, false>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream); }
             else      { if (az) launch_replay_c<CONTRACT_EXACT, true>(rough, model, P, d_ray0, t4, d_off, d_order, d.rec, d.stream);
@@ -1189,7 +1190,9 @@ extern "C" int altb_draws_lobe(altb_ctx* ctx, uint64_t seed, uint64_t ray_id0, u
     CK(cudaSetDevice(d.dev));
     float* buf = nullptr;
     CK(cudaMalloc(&buf, n * 8 * sizeof(float)));
-    if (ctx->contract == ALTB_CONTRACT_FAST)
+    if (ctx->contract == ALTB_CONTRACT_FAST7)
+        k_draws<CONTRACT_FAST7><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
+    else if (ctx->contract == ALTB_CONTRACT_FAST)
         k_draws<CONTRACT_FAST><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);
     else
         k_draws<CONTRACT_EXACT><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(philox_expand(seed), d.sincos, ray_id0, (uint32_t)n, k, lobe_n, (float)(lobe_deg * PI_D / 180.0), buf);

@@ -43,7 +43,7 @@ def workload_config(args, mode_name, world):
     return {"workload": "C3 nonLambertianFlux: CustomMirror BRDF (0.3,0.4,0.6), theta_max=170, rho=0.99, "
                         "sigma=0.01, src(-60,0,-75) dir(5,0,0), 180x90 map",
             "rays_per_step": total, "rays_per_gpu_per_step": total // world, "map_mode": mode_name, "seed": 4357,
-            "contract": getattr(args, "contract", "fast"),
+            "contract": getattr(args, "contract", "fast7"),
             "l2": "no input to cache: the RNG is counter-based and every step traces NEW ray ids, so nothing a step reads "
                   "was produced by an earlier one; per-step device traffic is the map/stats buffer only"}
 
@@ -212,7 +212,7 @@ def _run_ours(args):
     mode = A.MAP_DIRECTION if args.map == "direction" else A.MAP_LINE
     sc, src, mp = workload_scene(A), A.source(), A.map_spec(mode=mode)
     ctx = A.Context([local])
-    ctx.set_contract(A.CONTRACT_FAST if args.contract == "fast" else A.CONTRACT_EXACT)
+    ctx.set_contract({"fast": A.CONTRACT_FAST, "fast7": A.CONTRACT_FAST7, "exact": A.CONTRACT_EXACT}[args.contract])
     tr = ShardedTracer(ctx, sc, src, mp, seed=4357, device=local)
     nb = mp.n_theta * mp.n_phi
     next_id = [0]
@@ -298,7 +298,7 @@ def _run_ours(args):
             try:
                 t0 = time.perf_counter()
                 with A.Context(list(range(world))) as many:
-                    many.set_contract(A.CONTRACT_FAST if args.contract == "fast" else A.CONTRACT_EXACT)
+                    many.set_contract({"fast": A.CONTRACT_FAST, "fast7": A.CONTRACT_FAST7, "exact": A.CONTRACT_EXACT}[args.contract])
                     t1 = time.perf_counter()
                     c_in, s_in = many.trace_fluxmap(sc, src, PROBE_RAYS, mp, seed=4357, ray_id0=0)
                     t2 = time.perf_counter()
@@ -389,9 +389,10 @@ def main():
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--map", choices=["direction", "line"], default="direction")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--contract", choices=["fast", "exact"], default="fast",
+    ap.add_argument("--contract", choices=["fast7", "fast", "exact"], default="fast7",
                     help="arithmetic contract of the bounce loop (include/altair_b200.h): fast = MUFU special functions, validated by "
-                         "the north star's replay (<= 1e-4) and chi^2 criteria; exact = bit-identical to the CPU oracle")
+                         "the north star's replay (<= 1e-4) and chi^2 criteria; fast7 = fast + Philox4x32-7 as the generator (another "
+                         "random stream, validated statistically); exact = bit-identical to the CPU oracle")
     ap.add_argument("--ref-rays", type=int, default=0, help="CPU sample size (rays per step); 0 = sized from a calibration run")
     ap.add_argument("--ref-budget", type=float, default=90.0, help="seconds the reference arm may spend on its K steps")
     ap.add_argument("--no-cpu", action="store_true")

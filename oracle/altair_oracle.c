@@ -318,9 +318,20 @@ static inline void sincos2pi_d(double u, double* s, double* c) { double x = 2.0 
 static inline void sincos_d(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 
 /* ------------------------------------------------------------------ Philox + draws */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* rounds of the generator behind orc_draws / orc_trace: 10 (default; contracts EXACT and FAST of the library) or 7
+ * (ALTB_CONTRACT_FAST7: the fewest rounds that pass BigCrush, Salmon et al. 2011 table 2).  Process-wide, test infrastructure. */
+static int g_philox_rounds = 10;
+int orc_set_philox_rounds(int rounds) {
+    if (rounds != 7 && rounds != 10) return -1;
+    g_philox_rounds = rounds;
+    return 0;
+}
+static void philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds);
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_r(ctr, key, out, 10); }
+void orc_philox4x32_7(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_r(ctr, key, out, 7); }
+static void philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -342,7 +353,7 @@ static void draws_blk(uint64_t seed, uint64_t ray_id, uint32_t k, uint32_t blk, 
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {(uint32_t)ray_id, (uint32_t)(ray_id >> 32), k, blk};
     uint32_t w[4];
-    orc_philox4x32_10(ctr, key, w);
+    philox4x32_r(ctr, key, w, g_philox_rounds);
     out[0] = (float)(w[0] >> 8) * 0x1p-24f;
     out[1] = (float)(w[1] >> 8) * 0x1p-24f;
     out[2] = (float)(w[2] >> 12) * 0x1p-20f;

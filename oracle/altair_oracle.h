@@ -92,8 +92,11 @@ enum { ORC_F64 = 0, ORC_F32 = 1 };
  * all derived from ONE Philox4x32-10 block per hit (bit budget in altair_oracle.c:orc_draws);
  * u_* uniform on [0,1); g0,g1 independent N(0,1) (Box-Muller). */
 
-/* Philox4x32-10 (Salmon et al. 2011), one block. */
+/* Philox4x32-10 / -7 (Salmon et al. 2011), one block. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_philox4x32_7(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* rounds behind orc_draws / orc_trace / orc_fluxmap: 10 (default) or 7 (mirror of ALTB_CONTRACT_FAST7); process-wide */
+int orc_set_philox_rounds(int rounds);
 
 /* The 8 f32 draws for (seed, ray_id, hit index k) exactly as the CUDA kernels derive them. */
 void orc_draws(uint64_t seed, uint64_t ray_id, uint32_t k, float out[ORC_DRAWS_PER_HIT]);

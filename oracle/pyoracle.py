@@ -94,6 +94,7 @@ def lib():
     L = C.CDLL(_LIB)
     P = C.POINTER
     L.orc_philox4x32_10.argtypes = [P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]
+    L.orc_philox4x32_7.argtypes = [P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]
     L.orc_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, P(C.c_float)]
     L.orc_draws_lobe.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_float, P(C.c_float)]
     L.orc_sincos2pi_f32.argtypes = [C.c_float, P(C.c_float), P(C.c_float)]
@@ -134,11 +135,11 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
     o = (C.c_uint32 * 4)()
-    lib().orc_philox4x32_10(c, k, o)
+    (lib().orc_philox4x32_10 if rounds == 10 else lib().orc_philox4x32_7)(c, k, o)
     return list(o)
 
 
@@ -233,6 +234,11 @@ def disk_hits(sc, rec, centers, rots, det_r=5.0, det_halfthick=0.1):
     if rc:
         raise RuntimeError(f"orc_disk_hits rc={rc}")
     return hits
+
+
+def set_philox_rounds(rounds):
+    """10 (default) or 7 (mirror of the library's CONTRACT_FAST7); process-wide."""
+    assert lib().orc_set_philox_rounds(int(rounds)) == 0
 
 
 def count_horizon(sc, src, n, seed=4357, ray_id0=0, prec=F32):

@@ -27,6 +27,13 @@ def fast(ctx, altb):
     ctx.set_contract(altb.CONTRACT_EXACT)
 
 
+@pytest.fixture(params=["FAST", "FAST7"])
+def fast_any(request, ctx, altb):
+    ctx.set_contract(getattr(altb, "CONTRACT_" + request.param))
+    yield ctx
+    ctx.set_contract(altb.CONTRACT_EXACT)
+
+
 def test_contract_switch_and_draws(ctx, altb, oracle):
     exact = ctx.draws(SEED, 1 << 33, 200_000, 5)
     ctx.set_contract(altb.CONTRACT_FAST)
@@ -97,13 +104,35 @@ def test_fast_trace_against_exact_trace_per_ray(ctx, altb, kw):
     assert abs(e_st["n_bounces"] - f_st["n_bounces"]) <= 3e-4 * e_st["n_bounces"]
 
 
-def test_fast_statistics_against_independent_exact_run(ctx, altb):
+def test_fast7_draws_bit_exact_against_the_seven_round_oracle(ctx, altb, oracle):
+    """CONTRACT_FAST7 = the fast contract's arithmetic on the Philox4x32-7 stream: every integer field of the draw record
+    equals the CPU restatement with seven rounds bit for bit (the Gaussian deviates to MUFU accuracy)."""
+    ctx.set_contract(altb.CONTRACT_FAST7)
+    oracle.set_philox_rounds(7)
+    try:
+        assert ctx.contract == altb.CONTRACT_FAST7
+        for k in (0, 5, 49_999):
+            g = ctx.draws(SEED, (1 << 33) + 11, 4096, k)
+            o = np.stack([oracle.draws(SEED, (1 << 33) + 11 + i, k) for i in range(4096)])
+            assert np.array_equal(g[:, :5].view(np.uint32), o[:, :5].view(np.uint32)), k
+            rad = np.hypot(o[:, 5].astype(np.float64), o[:, 6])
+            dg = np.abs(g[:, 5:7].astype(np.float64) - o[:, 5:7])
+            assert dg[rad > 0.05].max() <= 5e-5 and dg.max() <= 1e-3
+    finally:
+        oracle.set_philox_rounds(10)
+        ctx.set_contract(altb.CONTRACT_EXACT)
+    # ... and it is another stream than the ten-round one
+    assert not np.array_equal(g[:, :5], ctx.draws(SEED, (1 << 33) + 11, 4096, 49_999)[:, :5])
+
+
+@pytest.mark.parametrize("which", ["FAST", "FAST7"])
+def test_fast_statistics_against_independent_exact_run(ctx, altb, which):
     """Statistical mode of the north star: INDEPENDENT samples (different ray ids) under the two contracts; every bin within
     Poisson errors (chi^2/ndf ~ 1, max |z| < 5.5 over ~14 000 populated bins), port fraction within 0.1 %."""
     n = 200_000_000
     sc, src, mp = altb.scene(theta_max=170.0, brdf_kind=1), altb.source(), altb.map_spec(mode=altb.MAP_DIRECTION)
     e_counts, e_st = ctx.trace_fluxmap(sc, src, n, mp, seed=SEED, ray_id0=0)
-    ctx.set_contract(altb.CONTRACT_FAST)
+    ctx.set_contract(getattr(altb, "CONTRACT_" + which))
     try:
         f_counts, f_st = ctx.trace_fluxmap(sc, src, n, mp, seed=SEED, ray_id0=n)
     finally:
@@ -119,9 +148,10 @@ def test_fast_statistics_against_independent_exact_run(ctx, altb):
     assert abs(bf / be - 1.0) < 5e-4
 
 
-def test_fast_sinks_agree_and_batched(fast, altb):
+def test_fast_sinks_agree_and_batched(fast_any, altb):
     """Under one contract the in-kernel direction sink, the batched launch and the record sink + map kernel are the same
     arithmetic: identical integer maps."""
+    fast = fast_any
     n = 300_000
     mp = altb.map_spec(mode=altb.MAP_DIRECTION)
     thetas = (160.0, 170.0, 175.0)

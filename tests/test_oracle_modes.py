@@ -13,6 +13,30 @@ def test_philox4x32_10_known_answers(oracle):
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
+def test_philox4x32_7_known_answers_and_round_switch(oracle):
+    """Random123 kat_vectors for philox4x32-7 (the generator of the library's CONTRACT_FAST7), and the process-wide switch
+    that makes orc_draws / orc_trace use it."""
+    assert oracle.philox([0, 0, 0, 0], [0, 0], rounds=7) == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2, rounds=7) == [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], rounds=7) == \
+        [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]
+    d10 = oracle.draws(4357, 12345, 3)
+    oracle.set_philox_rounds(7)
+    try:
+        d7 = oracle.draws(4357, 12345, 3)
+        w = oracle.philox([12345, 0, 3, 0], [4357, 0], rounds=7)
+        assert d7[0] == np.float32((w[0] >> 8) * 2.0 ** -24) and d7[2] == np.float32((w[2] >> 12) * 2.0 ** -20)
+        # the physics does not care: same escape fraction and hit count within sampling error
+        _, s7 = oracle.trace(oracle.scene(theta_max=170.0), oracle.source(), 150_000, seed=8, prec=oracle.F64)
+    finally:
+        oracle.set_philox_rounds(10)
+    assert not np.array_equal(d7, d10) and np.array_equal(oracle.draws(4357, 12345, 3), d10)
+    _, s10 = oracle.trace(oracle.scene(theta_max=170.0), oracle.source(), 150_000, seed=8, prec=oracle.F64)
+    p7, p10 = s7["n_exit_port"] / 150_000, s10["n_exit_port"] / 150_000
+    assert abs(p7 - p10) < 4 * np.sqrt(2 * 0.2445 / 150_000) and s7["n_exit_port"] != s10["n_exit_port"]
+    assert abs(s7["n_bounces"] / s10["n_bounces"] - 1) < 4 * np.sqrt(2.0 / 150_000)
+
+
 def test_f32_primitives_accuracy(oracle):
     L = oracle.lib()
     rng = np.random.default_rng(0)

@@ -26,7 +26,7 @@ ap.add_argument("--rays", type=int, default=100_000_000)
 ap.add_argument("--out", default="")
 ap.add_argument("--shard", choices=["rays", "scenes"], default="rays",
                 help="N>1: split every scene's rays over the ranks, or deal whole scenes round-robin (measured on 8 B200: 0.448 s vs 0.454 s)")
-ap.add_argument("--contract", default="fast", choices=["exact", "fast"])
+ap.add_argument("--contract", default="fast", choices=["exact", "fast", "fast7"])
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -34,7 +34,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 thetas = [100.0 + 0.5 * k for k in range(a.scenes)]
 ctx = A.Context([local])
-ctx.set_contract(A.CONTRACT_FAST if a.contract == "fast" else A.CONTRACT_EXACT)
+ctx.set_contract({"fast": A.CONTRACT_FAST, "fast7": A.CONTRACT_FAST7, "exact": A.CONTRACT_EXACT}[a.contract])
 tr = ShardedTracer(ctx, [A.scene(theta_max=t) for t in thetas], A.source(), A.map_spec(mode=A.MAP_DIRECTION), device=local, shard=a.shard)
 tr.step(min(a.rays, 1_000_000))                      # warm-up
 torch.cuda.synchronize()

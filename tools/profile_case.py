@@ -16,12 +16,12 @@ ap.add_argument("--rho", type=float, default=0.99)
 ap.add_argument("--theta", type=float, default=170.0)
 ap.add_argument("--limit", type=int, default=50000)
 ap.add_argument("--sigma", type=float, default=0.01)
-ap.add_argument("--contract", default="fast", choices=["exact", "fast"])
+ap.add_argument("--contract", default="fast", choices=["exact", "fast", "fast7"])
 ap.add_argument("--batch", type=int, default=0, help="rays per launch (0: library default 2^26)")
 a = ap.parse_args()
 mode = {"direction": A.MAP_DIRECTION, "line": A.MAP_LINE, "compat": A.MAP_TRACEONCE_COMPAT}[a.map]
 with A.Context([0]) as ctx:
-    ctx.set_contract(A.CONTRACT_FAST if a.contract == "fast" else A.CONTRACT_EXACT)
+    ctx.set_contract({"fast": A.CONTRACT_FAST, "fast7": A.CONTRACT_FAST7, "exact": A.CONTRACT_EXACT}[a.contract])
     if a.batch:
         ctx.set_batch(a.batch)
     for r in range(a.reps):
