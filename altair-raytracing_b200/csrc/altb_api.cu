@@ -434,7 +434,9 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
         else          { if (ts.model == 0) GEN(false, 0); else if (ts.model == 1) GEN(false, 1); else if (ts.model == 2) GEN(false, 2); else GEN(false, 3); }
 #undef GEN
     } else {
-        const bool fast = ctx->contract != ALTB_CONTRACT_EXACT && ts.model <= 1;      // other models: exact instances only
+        // fast instances: Lambert / CustomMirror with the small-angle flags their hot loop has compiled in (bounce_step)
+        const bool fast = ctx->contract != ALTB_CONTRACT_EXACT && ts.model <= 1 && (!ts.rough || P.k.tilt_small == 2) &&
+                          (ts.model != 1 || P.k.spec_small == 1);
         le = !fast ? launch_trace_c<CONTRACT_EXACT>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
            : ctx->contract == ALTB_CONTRACT_FAST7 ? launch_trace_c<CONTRACT_FAST7>(sink, ts.rough, ts.model, P, rec, counter, blocks, st)
                                                   : launch_trace_c<CONTRACT_FAST>(sink, ts.rough, ts.model, P, rec, counter, blocks, st);

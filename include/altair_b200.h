@@ -108,8 +108,9 @@ int  altb_set_batch(altb_ctx* ctx, uint64_t batch_rays);
  * ALTB_CONTRACT_FAST: the same algorithm and the same random integers, with sqrt / reciprocal / log / sin / cos taken
  *   straight from the GPU's special-function unit (relative error ~1e-7).  Results agree with the exact contract the way
  *   BASELINE.json's north star defines agreement: per-ray replay against the double-precision CPU path differs for
- *   <= 1e-4 of the rays, maps agree statistically (chi^2/ndf ~ 1).  Built for brdf_kind 0 and 1 with lambertian = 1; other
- *   scenes, rim-aimed sources and altb_trace_paths always use the exact contract.
+ *   <= 1e-4 of the rays, maps agree statistically (chi^2/ndf ~ 1).  Built for brdf_kind 0 and 1 with lambertian = 1,
+ *   roughness_rad <= 0.0114 (the reference's production scenes have 0.01 or 0) and a kind-1 lobe parameter <= 0.325 (0.3);
+ *   other scenes, rim-aimed sources and altb_trace_paths always use the exact contract.
  * ALTB_CONTRACT_FAST7: the fast contract's arithmetic, with Philox4x32-7 instead of Philox4x32-10 as the generator (seven rounds
  *   are the fewest that pass BigCrush: Salmon et al. 2011; ten carry a safety margin).  Another random stream: results agree
  *   with the other contracts statistically, not per ray; altb_draws returns this stream and is checked bit for bit.  Replay

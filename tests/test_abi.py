@@ -82,3 +82,9 @@ def test_hot_loop_has_no_spills(altb):
     want = {f"1,{m},{s}" for m in (0, 1) for s in (0, 1, 2)}
     assert set(inside) >= want, out
     assert all(inside[k] <= 4 for k in want), out
+    # the fast contracts' instances (sink 3: the LINES sink as well)
+    for label in ("fast", "fast7"):
+        got = {m.group(1): int(m.group(2)) for m in re.finditer(r"k_trace<(\d,\d,\d)> %s:.*?: (\d+) in the bounce bodies" % label, out)}
+        want_f = {f"1,{m},{s}" for m in (0, 1) for s in (0, 1, 2, 3)}
+        assert set(got) >= want_f, out
+        assert all(got[k] <= 4 for k in want_f), (label, out)

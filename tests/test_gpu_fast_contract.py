@@ -164,3 +164,21 @@ def test_fast_sinks_agree_and_batched(fast_any, altb):
         assert np.array_equal(b_counts[i], s_counts[0]) and np.array_equal(s_counts[0], m_counts)
         for key in ("n_rays", "n_exited", "n_exit_port", "n_absorbed", "n_suspended", "n_bounces"):
             assert b_st[i][key] == s_st[0][key] == r_st[key], key
+
+
+@pytest.mark.parametrize("kw", [dict(theta_max=170.0, roughness=0.05), dict(theta_max=170.0, brdf_kind=1, brdf_param=(0.5, 0.4, 0.6, 0.0)),
+                                dict(theta_max=170.0, world_half=200.0, reflectance=1.0, roughness=0.5, max_bounces=10000)])
+def test_fast_contracts_fall_back_to_exact_outside_their_scenes(fast_any, altb, oracle, kw):
+    """The fast contracts' hot loop has the small-angle evaluation of the roughness tilt and of the specular lobe compiled in
+    (roughness <= 0.0114 rad, lobe parameter <= 0.325: the reference's production scene).  Any other scene runs the exact
+    contract whatever the context's setting: bit-identical to the oracle."""
+    n = 60_000
+    g_rec, g_st = fast_any.trace_records(altb.scene(**kw), altb.source(), n, seed=SEED)
+    o_rec, o_st = oracle.trace(oracle.scene(**kw), oracle.source(), n, seed=SEED, prec=oracle.F32)
+    for f in ("pos", "dir"):
+        assert np.array_equal(g_rec[f].view(np.uint32), o_rec[f].view(np.uint32)), f
+    assert np.array_equal(g_rec["n_hits"], o_rec["n_hits"]) and np.array_equal(g_rec["status"], o_rec["status"])
+    mp = altb.map_spec(mode=altb.MAP_DIRECTION)
+    g_counts, _ = fast_any.trace_fluxmap(altb.scene(**kw), altb.source(), n, mp, seed=SEED)
+    o_counts, _ = oracle.fluxmap(oracle.scene(**kw), oracle.source(), n, oracle.map_spec(mode=oracle.MAP_DIRECTION), seed=SEED, prec=oracle.F32)
+    assert np.array_equal(g_counts[0], o_counts)

@@ -11,6 +11,7 @@ if [ "$2" != "skip-tests" ]; then
 fi
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench.err; echo "reference arm rc=$?"
 timeout 600 python bench.py > $out/${tag}_bench.json 2>> $out/${tag}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --contract fast --no-cpu > $out/${tag}_bench_fast.json 2>> $out/${tag}_bench.err; echo "bench fast rc=$?"
 timeout 600 python bench.py --contract exact --no-cpu > $out/${tag}_bench_exact.json 2>> $out/${tag}_bench.err; echo "bench exact rc=$?"
 timeout 600 python bench.py --map line --rays 100000000 --no-cpu > $out/${tag}_bench_line.json 2>> $out/${tag}_bench.err; echo "bench line rc=$?"
 timeout 300 python tools/port_angle_sweep.py --out $out/${tag}_c5.json > $out/${tag}_c5.log 2>&1; echo "c5 rc=$?"; head -1 $out/${tag}_c5.log
@@ -18,7 +19,8 @@ timeout 300 python tools/port_angle_sweep.py --contract exact --out $out/${tag}_
 timeout 300 python tools/detector_sweep_bench.py > $out/${tag}_c4.log 2>&1; tail -2 $out/${tag}_c4.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu > $out/${tag}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_line.csv python bench.py --map line --rays 100000000 --steps 2 --warmup 3 --no-cpu > $out/${tag}_ncu_line.log 2>&1; echo "ncu list line rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -o $out/${tag}_ktrace_fast python tools/profile_case.py --rays 268435456 --reps 1 --contract fast > $out/${tag}_ncu_fast.log 2>&1; echo "ncu fast rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -o $out/${tag}_ktrace_exact python tools/profile_case.py --rays 268435456 --reps 1 --contract exact > $out/${tag}_ncu_exact.log 2>&1; echo "ncu exact rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_map_line_rect|k_prepare_lines|k_map_line" -c 3 -o $out/${tag}_linemap python tools/profile_case.py --rays 100000000 --reps 1 --map line > $out/${tag}_ncu_linemap.log 2>&1; echo "ncu linemap rc=$?"
+for c in fast7 exact; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -o $out/${tag}_ktrace_$c python tools/profile_case.py --rays 268435456 --reps 1 --contract $c > $out/${tag}_ncu_$c.log 2>&1; echo "ncu $c rc=$?"
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_map_line_rect|k_prepare_raw|k_map_line" -c 3 -o $out/${tag}_linemap python tools/profile_case.py --rays 100000000 --reps 1 --map line > $out/${tag}_ncu_linemap.log 2>&1; echo "ncu linemap rc=$?"
 ls -la $out | tail -30

@@ -38,6 +38,7 @@ hdr = rows[1]
 ia, ie, it = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
 base = None
 per_line, per_file = defaultdict(lambda: [0, 0]), defaultdict(lambda: [0, 0])
+per_op = defaultdict(int)          # dynamic warp-instructions per SASS opcode (predicate and modifiers stripped)
 tot = tott = 0
 for r in rows[2:]:
     try:
@@ -47,7 +48,9 @@ for r in rows[2:]:
     if base is None:
         base = a
     off = a - base
-    loc = lines.get(off, (("?", 0), ""))[0]
+    loc, ins = lines.get(off, (("?", 0), ""))
+    op = re.sub(r"^@!?U?P\d+\s+", "", ins).split(" ")[0].split(".")[0] if ins else "?"
+    per_op[op] += e
     per_line[loc][0] += e; per_line[loc][1] += t
     per_file[loc[0]][0] += e; per_file[loc[0]][1] += t
     tot += e; tott += t
@@ -79,6 +82,10 @@ print("by function:")
 for (fn, f), (e, t) in sorted(per_func.items(), key=lambda x: -x[1][0])[:40]:
     extra = f"  {e / unit:7.2f} per unit" if unit else ""
     print(f"  {e / tot * 100:5.2f}%  thr {t / max(e, 1):4.1f}{extra}  {fn}:{f}")
+print("by opcode:")
+for op, e in sorted(per_op.items(), key=lambda x: -x[1])[:32]:
+    extra = f"  {e / unit:7.2f} per unit" if unit else ""
+    print(f"  {e / tot * 100:5.2f}%{extra}  {op}")
 print("top lines:")
 for (fn, ln), (e, t) in sorted(per_line.items(), key=lambda x: -x[1][0])[:top]:
     print(f"  {e / tot * 100:5.2f}%  thr {t / max(e, 1):4.1f}  {fn}:{ln}  {text(fn, ln)}")

@@ -16,7 +16,7 @@ ap.add_argument("--rho", type=float, default=0.99)
 ap.add_argument("--theta", type=float, default=170.0)
 ap.add_argument("--limit", type=int, default=50000)
 ap.add_argument("--sigma", type=float, default=0.01)
-ap.add_argument("--contract", default="fast", choices=["exact", "fast", "fast7"])
+ap.add_argument("--contract", default="fast7", choices=["exact", "fast", "fast7"])
 ap.add_argument("--batch", type=int, default=0, help="rays per launch (0: library default 2^26)")
 a = ap.parse_args()
 mode = {"direction": A.MAP_DIRECTION, "line": A.MAP_LINE, "compat": A.MAP_TRACEONCE_COMPAT}[a.map]

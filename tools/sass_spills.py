@@ -30,7 +30,7 @@ for name, ins in funcs.items():
             clusters.append([a, a, 0])
         clusters[-1][1] = a
         clusters[-1][2] += 1
-    big = [c for c in clusters if c[2] >= 20]                    # full 10-round blocks (20 wide multiplies)
+    big = [c for c in clusters if c[2] >= 14]                    # full Philox blocks (10 rounds: 20 wide multiplies; 7 rounds: 14)
     # bounce bodies: from the first Philox block of the hot loop to one body length past the last one
     hot = (0, 0)
     if len(big) >= 2:
@@ -42,5 +42,5 @@ for name, ins in funcs.items():
     loc = [(a, t) for a, t in ins if re.search(r"\b(STL|LDL)", t)]
     inside = [a for a, t in loc if hot[0] <= a <= hot[1]]
     tag = re.search(r"k_traceILb(\d)ELi(\d)ELi(\d)ELi(\d)", name)
-    print(f"k_trace<{tag.group(1)},{tag.group(2)},{tag.group(3)}>{'' if tag.group(4) == '0' else ' fast'}: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
+    print(f"k_trace<{tag.group(1)},{tag.group(2)},{tag.group(3)}>{('', ' fast', ' fast7')[int(tag.group(4))]}: {len(ins)} instructions, hot loop {hot[0]:#x}..{hot[1]:#x}, "
           f"local-memory instructions: {len(inside)} in the bounce bodies, {len(loc) - len(inside)} elsewhere")
