@@ -1,12 +1,12 @@
 #!/bin/bash
-# multi-GPU checks on one box: usage tools/gpu_multi.sh <N> <tag>
+# multi-GPU checks on one box: usage [SKIP_REF=1] [SKIP_EXACT=1] tools/gpu_multi.sh <N> <tag>   (an 8-GPU box is charged 8 x: the CPU reference arm alone is 12 GPU-minutes there)
 N=${1:-2}; tag=${2:-m}; out=gpurun_out; mkdir -p $out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 nvidia-smi -L | head -$N
 timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "multi_device" 2>&1 | tail -3
-timeout 600 $TR bench.py --gpus $N --impl reference --steps 5 --warmup 1 > $out/${tag}_ref_n$N.json 2> $out/${tag}_ref_n$N.err; echo "reference arm N=$N rc=$?"; cut -c1-300 $out/${tag}_ref_n$N.json
+[ -z "$SKIP_REF" ] && timeout 600 $TR bench.py --gpus $N --impl reference --steps 5 --warmup 1 > $out/${tag}_ref_n$N.json 2> $out/${tag}_ref_n$N.err; echo "reference arm N=$N rc=$?"; cut -c1-300 $out/${tag}_ref_n$N.json
 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 > $out/${tag}_bench_n$N.json 2> $out/${tag}_bench_n$N.err; echo "bench N=$N rc=$?"
-timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --contract exact --no-other > $out/${tag}_bench_exact_n$N.json 2>> $out/${tag}_bench_n$N.err; echo "bench exact N=$N rc=$?"
+[ -z "$SKIP_EXACT" ] && timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --contract exact --no-other > $out/${tag}_bench_exact_n$N.json 2>> $out/${tag}_bench_n$N.err; echo "bench exact N=$N rc=$?"
 timeout 600 $TR tools/port_angle_sweep.py --out $out/${tag}_c5_n$N.json > $out/${tag}_c5_n$N.log 2>&1; head -1 $out/${tag}_c5_n$N.log
 timeout 600 python - <<'PY' > $out/${tag}_macro_n${N}.log 2>&1
 # the C++ macro mirror with threads = N (one process, N GPUs, NCCL inside the C ABI) against threads = 1: byte-identical CSV
