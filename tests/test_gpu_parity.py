@@ -585,9 +585,13 @@ def test_polylines_bit_exact(ctx, oracle, altb):
         assert np.allclose(r, 100.1, atol=1e-4)                                              # hits lie on the inner sphere
 
 
-@pytest.mark.parametrize("nt,npb,width", [(1, 1, 40.0), (7, 3, 40.0), (90, 45, 10.0), (181, 91, 40.0), (33, 2, 5.0), (2, 64, 60.0)])
+@pytest.mark.parametrize("nt,npb,width", [(1, 1, 40.0), (7, 3, 40.0), (90, 45, 10.0), (181, 91, 40.0), (33, 2, 5.0), (2, 64, 60.0),
+                                          (17, 250, 25.0), (250, 9, 80.0), (251, 33, 120.0)])
 def test_line_map_odd_grids(ctx, oracle, altb, nt, npb, width):
-    """Tile / super-tile culling must stay conservative for any grid shape (partial tiles, single rows, odd sizes)."""
+    """Tile / super-tile culling must stay conservative for any grid shape (partial tiles, single rows, odd sizes); the
+    row-stationary rectangle kernel must cope with rectangles of more than 32 columns (column chunks: 250 columns at the
+    pole), of more than 32 row pairs (row blocks: an 80 cm detector on 0.36 deg rows) and with a last row pair that has no
+    second row (odd n_theta)."""
     n = 12_000
     for mode in ("LINE", "TRACEONCE_COMPAT"):
         g, _ = ctx.trace_fluxmap(altb.scene(theta_max=168.0), altb.source(), n, altb.map_spec(nt, npb, 100.0, width, getattr(altb, "MAP_" + mode)), seed=5)

@@ -11,7 +11,7 @@ import altair_raytracing_b200 as A  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60_000
 with A.Context([0]) as ctx:
-    for contract in (A.CONTRACT_EXACT, A.CONTRACT_FAST):
+    for contract in (A.CONTRACT_EXACT, A.CONTRACT_FAST, A.CONTRACT_FAST7):
         ctx.set_contract(contract)
         for mode in (A.MAP_DIRECTION, A.MAP_LINE, A.MAP_TRACEONCE_COMPAT):
             c, st = ctx.trace_fluxmap(A.scene(brdf_kind=1), A.source(), n, A.map_spec(mode=mode), seed=1)
@@ -22,6 +22,17 @@ with A.Context([0]) as ctx:
         c, st = ctx.trace_fluxmap(A.scene(count_all_status=1, theta_max=178.0), A.source(), n // 4, A.map_spec(33, 7, 100.0, 30.0, A.MAP_LINE), seed=3)
         print("odd grid / count_all", int(c.sum()))
     ctx.set_contract(A.CONTRACT_EXACT)
+    # LINE maps of odd shapes through the row-stationary kernel: narrow / wide detectors (few / many row pairs per cap, more
+    # than 32 columns per rectangle at the pole), odd n_theta (a last row pair without a second row), odd n_phi
+    for nt, npb, w in ((180, 90, 40.0), (45, 20, 10.0), (181, 91, 60.0), (17, 250, 25.0), (250, 9, 80.0)):
+        c, st = ctx.trace_fluxmap(A.scene(), A.source(), n // 2, A.map_spec(nt, npb, 100.0, w, A.MAP_LINE), seed=7)
+        print("line", nt, npb, w, int(c.sum()))
+    # brdf_kind 3 (post-hoc re-scatter + second trace) and the horizon diagnostic
+    kw = dict(theta_max=140.0, world_half=103.0, r_outer=102.5, reflectance=0.95, roughness=0.2, count_all_status=1, brdf_kind=3,
+              brdf_param=(1.0, 1.0, 0.0, 0.0))
+    rec, st = ctx.trace_records(A.scene(**kw), A.source(), n // 4, seed=8)
+    c, st2 = ctx.trace_fluxmap(A.scene(**kw), A.source(), n // 4, A.map_spec(45, 20, 100.0, 10.0, A.MAP_LINE), seed=8)
+    print("posthoc", st["n_bounces"], int(c.sum()), "horizon", ctx.count_horizon(A.scene(roughness=0.5), A.source(), n // 4))
     rec, st = ctx.trace_records(A.scene(), A.source(), n // 4, seed=4)
     c = ctx.map_records(A.scene(), A.map_spec(20, 10, 100.0, 40.0, A.MAP_PER_POSITION, rays_per_position=50), rec)
     print("records", st["n_bounces"], "per-position", int(c.sum()))
