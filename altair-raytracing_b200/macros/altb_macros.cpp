@@ -130,6 +130,10 @@ struct Ctx {
             else altb_set_batch(slot, 1ull << 26);
         }
         h = slot;
+        if (h && altb_set_contract(h, settings().contract) != 0) {      // Settings::contract: the arithmetic contract of every call
+            std::cerr << "Error: " << altb_last_error() << std::endl;
+            h = nullptr;
+        }
     }
 };
 
@@ -595,6 +599,7 @@ int altbm_set(const char* key, double v) {
     else if (k == "distribution_rays") S.distribution_rays = (int)v;
     else if (k == "nonlambertian_rays") S.nonlambertian_rays = (int)v;
     else if (k == "nonlambertian_posthoc") S.nonlambertian_posthoc = (int)v;
+    else if (k == "contract") S.contract = (int)v;
     else if (k == "next_ray_id") S.next_ray_id = (uint64_t)v;
     else if (k == "advance_ray_ids") S.advance_ray_ids = (int)v;
     else if (k == "seed") S.seed = (uint64_t)v;

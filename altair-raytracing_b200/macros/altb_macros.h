@@ -46,6 +46,8 @@ struct Settings {
     int advance_ray_ids = 1;
     int traceonce_as_shipped = 1;     // 1: reproduce the published trace-once maps (line from the origin);
                                       // 0: the intended semantics (true final segment)
+    int contract = 0;                 // ALTB_CONTRACT_EXACT (bit-identical to the CPU oracle; default), 1 = _FAST, 2 = _FAST7
+                                      // (include/altair_b200.h): the macros' maps agree statistically, not ray by ray
     int verbose = 1;
     std::string output_dir;           // prefix for relative output paths ("" = current directory, as the reference)
 };

@@ -179,6 +179,29 @@ def test_nonLambertianFlux_posthoc_and_per_bounce(M, oracle):
         M.altbm_set(b"nonlambertian_rays", 100000); M.altbm_set(b"nonlambertian_posthoc", 1)
 
 
+def test_macro_contract_setting(M, oracle):
+    """Settings::contract: the macros run under the exact contract by default (CSV = oracle bit for bit, the tests above);
+    with contract = 2 (fast arithmetic + Philox4x32-7) the same call gives another sample of the same map."""
+    n = 400_000
+    M.altbm_set(b"traceonce_rays", n)
+    try:
+        M.altbm_sweepDetectorTraceOnce(0, b"c0", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+        a = _rows(M.altbm_last_csv().decode())[:, 2]
+        M.altbm_set(b"contract", 2)
+        M.altbm_sweepDetectorTraceOnce(0, b"c2", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+        b = _rows(M.altbm_last_csv().decode())[:, 2]
+        assert M.altbm_set(b"contract", 9) == 0          # accepted by the setter; the next call reports the library's error
+        M.altbm_sweepDetectorTraceOnce(0, b"c9", 1, -60.0, 0.0, -75.0, 5.0, 0.0, 0.0, 170.0)
+    finally:
+        M.altbm_set(b"contract", 0); M.altbm_set(b"traceonce_rays", 100000)
+    assert not np.array_equal(a, b)
+    assert abs(b.sum() / a.sum() - 1) < 0.01              # 3.2e6 hits each, ~270 correlated hits per escaping ray
+    k1, k2 = np.rint(a * n), np.rint(b * n)
+    use = k1 + k2 > 200
+    z = (k1[use] - k2[use]) / np.sqrt(k1[use] + k2[use])
+    assert use.sum() > 5000 and (z ** 2).mean() < 1.8       # bins share rays (~60 effective degrees of freedom): no tighter than that
+
+
 def test_full_size_sweepDetector_against_reference_map(M, altb):
     """BASELINE-size statistical parity on the GPU: the production macro (fluxAtObserverOptimize.C sweepDetector:
     16 200 positions x 50 000 fresh rays = 8.1e8 rays; 12 524 s in the reference's own footer) against the reference's
