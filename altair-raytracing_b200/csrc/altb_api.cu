@@ -1032,9 +1032,10 @@ extern "C" int altb_detector_sweep(altb_ctx* ctx, const altb_scene* scene, const
             if (rc) break;
             k_stats<<<d.sm_count * 4, 256, 0, d.stream>>>(d.rec, n, ts.P.g.count_all, ts.P.k.exit_zf, d.stats);
             int blocks = d.sm_count * 4;
+            if (const char* e = getenv("ALTB_DISK_BLOCKS")) blocks = d.sm_count * std::max(1, atoi(e));      // tuning knob
             const int need = (int)((n + 7) / 8);
             if (blocks > need) blocks = need;
-            k_disk_hits<<<blocks, DISK_THREADS, (size_t)m * (sizeof(float4) + sizeof(unsigned int)), d.stream>>>(d.rec, n, ts.P.g, d_geo, d_geo + (size_t)m * 3, m, det_r,
+            k_disk_hits<<<blocks, DISK_THREADS, (size_t)m * sizeof(unsigned int), d.stream>>>(d.rec, n, ts.P.g, d_geo, d_geo + (size_t)m * 3, m, det_r,
                                                                                                    det_halfthick, d_hits);
             ctx->launches += 2;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ALTB_E_CUDA, "detector_sweep: launch failed");

@@ -1373,30 +1373,39 @@ __device__ __forceinline__ bool disk_hit(const Geom& g, const f3& ef, const f3& 
     return lo <= hi;
 }
 
-// Two stages per warp.  (1) FP32 pre-test, lanes = disks, one ray per pass: a hit needs the ray's LINE to pass within
-// sqrt(rad^2 + ht^2) of the disk centre (bounding sphere of the thin cylinder); evaluated in f32 with half a centimetre of
-// slack (coordinates <= a few hundred cm: the f32 error of the squared distance is < 0.1 cm^2) it rejects ~99 % of the
-// (ray, pose) pairs.  (2) The survivors are compacted (ballot + prefix popcount) into the warp's shared-memory queue and
-// the FP64 test runs on 32 of them at a time, hits going to a per-block shared histogram.  Counts are exactly those of
-// the FP64 test on every pair.
+// Two stages per warp.  (1) FP32 pre-test, POSE-stationary: every lane keeps DISK_PPL disk centres in registers (32 x 12 = 384 poses
+// per group: the reference's 362 are one group) and the warp streams the rays past them -- one uniform 32-byte load per ray, then
+// 12 independent 11-operation tests per lane, no shared-memory traffic, no vote (the first version walked the poses 32 at a time
+// per ray: a shared load, a ballot and a branch per chunk in one dependent chain -- 429 instructions per ray at 47 % of the issue
+// slots).  A hit needs the ray's LINE to pass within sqrt(rad^2 + ht^2) of the disk centre (bounding sphere of the thin cylinder);
+// evaluated in f32 with half a centimetre of slack (coordinates <= a few hundred cm: the f32 error of the squared distance is
+// < 0.1 cm^2) it rejects ~99 % of the (ray, pose) pairs.  (2) The survivors go to the warp's shared-memory queue (slot from a
+// per-warp shared counter) and the FP64 test runs on 32 of them at a time, hits going to a per-block shared histogram.  Counts
+// are exactly those of the FP64 test on every pair.
 static constexpr int DISK_THREADS = 256;
-__global__ void __launch_bounds__(DISK_THREADS) k_disk_hits(const altb_record* __restrict__ rec, uint32_t n, const Geom g,
+#ifndef ALTB_DISK_PPL
+#define ALTB_DISK_PPL 12
+#endif
+#ifndef ALTB_DISK_MINB
+#define ALTB_DISK_MINB 2
+#endif
+static constexpr int DISK_PPL = ALTB_DISK_PPL;                        // poses per lane and group
+static constexpr int DISK_QCAP = 32 + 32 * DISK_PPL;                  // a ray adds at most 32 * PPL pairs to a backlog of < 32
+__global__ void __launch_bounds__(DISK_THREADS, ALTB_DISK_MINB) k_disk_hits(const altb_record* __restrict__ rec, uint32_t n, const Geom g,
                                                             const double* __restrict__ centers, const double* __restrict__ rots,
                                                             uint32_t m, double rad, double ht,
                                                             unsigned long long* __restrict__ hits) {
-    extern __shared__ __align__(16) unsigned char disk_smem[];        // float4 centre[m] (f32 copy), then unsigned hist[m]
-    float4* s_cf = reinterpret_cast<float4*>(disk_smem);
-    unsigned int* disk_hist = reinterpret_cast<unsigned int*>(s_cf + m);
-    __shared__ uint2 s_pairs[DISK_THREADS / 32][64];                  // (record index, disk index)
-    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
-        disk_hist[j] = 0u;
-        s_cf[j] = make_float4((float)centers[3 * (size_t)j], (float)centers[3 * (size_t)j + 1], (float)centers[3 * (size_t)j + 2], 0.f);
-    }
+    extern __shared__ __align__(16) unsigned char disk_smem[];        // unsigned hist[m]
+    unsigned int* disk_hist = reinterpret_cast<unsigned int*>(disk_smem);
+    __shared__ uint2 s_pairs[DISK_THREADS / 32][DISK_QCAP];           // (record index, disk index)
+    __shared__ unsigned int s_cnt[DISK_THREADS / 32];
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) disk_hist[j] = 0u;
+    if (threadIdx.x < DISK_THREADS / 32) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    uint2* q = s_pairs[threadIdx.x >> 5];
-    uint32_t nq = 0;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint2* q = s_pairs[w];
+    volatile unsigned int* cnt_p = s_cnt + w;
     const float rb = (float)sqrt(rad * rad + ht * ht) + 0.5f;
     const float rb2 = rb * rb;
     auto exact = [&](uint32_t first, uint32_t cnt) {                   // FP64 test of queue entries [first, first+cnt), cnt <= 32
@@ -1407,33 +1416,44 @@ __global__ void __launch_bounds__(DISK_THREADS) k_disk_hits(const altb_record* _
             if (disk_hit(g, pos, dir, centers + 3 * (size_t)e.y, rots + 9 * (size_t)e.y, rad, ht)) atomicAdd(&disk_hist[e.y], 1u);
         }
     };
-    const uint32_t m_pad = (m + 31u) & ~31u;
-    for (size_t i = gw; i < n; i += nw) {                              // warp-uniform: every lane looks at the same ray
-        f3 pos, dir; uint32_t h, status;
-        load_record(rec, i, pos, dir, h, status);
-        if (status != ALTB_EXITED) continue;
-        for (uint32_t j = lane; j < m_pad; j += 32) {
-            bool cand = false;
-            if (j < m) {
-                const float4 c = s_cf[j];
-                const f3 mv = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
-                const float md = mv.x * dir.x + mv.y * dir.y + mv.z * dir.z;
-                cand = (mv.x * mv.x + mv.y * mv.y + mv.z * mv.z) - md * md <= rb2;      // |dir| = 1 up to f32 rounding
+    const uint32_t per_group = 32u * DISK_PPL;
+    for (uint32_t j0 = 0; j0 < m; j0 += per_group) {
+        float cx[DISK_PPL], cy[DISK_PPL], cz[DISK_PPL];
+#pragma unroll
+        for (int p = 0; p < DISK_PPL; p++) {
+            const uint32_t j = j0 + 32u * p + lane;
+            // poses beyond m: a centre no line comes near (3e18^2 is still finite in f32)
+            cx[p] = j < m ? (float)centers[3 * (size_t)j] : 3e18f;
+            cy[p] = j < m ? (float)centers[3 * (size_t)j + 1] : 3e18f;
+            cz[p] = j < m ? (float)centers[3 * (size_t)j + 2] : 3e18f;
+        }
+        // warp-uniform: every lane looks at the same ray; the next ray's record is in flight while this one is tested
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb4 = ra;
+        if (gw < n) { ra = __ldg(reinterpret_cast<const float4*>(rec + gw)); rb4 = __ldg(reinterpret_cast<const float4*>(rec + gw) + 1); }
+        for (size_t i = gw; i < n; i += nw) {
+            const f3 pos = {ra.x, ra.y, ra.z}, dir = {ra.w, rb4.x, rb4.y};
+            const uint32_t status = __float_as_uint(rb4.w);
+            if (i + nw < n) { ra = __ldg(reinterpret_cast<const float4*>(rec + i + nw)); rb4 = __ldg(reinterpret_cast<const float4*>(rec + i + nw) + 1); }
+            if (status != ALTB_EXITED) continue;
+#pragma unroll
+            for (int p = 0; p < DISK_PPL; p++) {
+                const f3 mv = {cx[p] - pos.x, cy[p] - pos.y, cz[p] - pos.z};
+                const float md = dot3(mv, dir);
+                if (fma_(-md, md, dot3(mv, mv)) <= rb2)                               // |dir| = 1 up to f32 rounding
+                    q[atomicAdd(&s_cnt[w], 1u)] = make_uint2((uint32_t)i, j0 + 32u * p + lane);
             }
-            const unsigned cm = __ballot_sync(FULL, cand);
-            if (cm) {
-                if (cand) q[nq + __popc(cm & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, j);
-                nq += __popc(cm);
+            __syncwarp();
+            uint32_t cnt = *cnt_p;
+            if (cnt >= 32u) {
+                do { cnt -= 32u; exact(cnt, 32u); } while (cnt >= 32u);
                 __syncwarp();
-                if (nq >= 32) {
-                    nq -= 32;
-                    exact(nq, 32);
-                    __syncwarp();
-                }
+                if (lane == 0) *cnt_p = cnt;
+                __syncwarp();
             }
         }
     }
-    exact(0, nq);
+    __syncwarp();
+    exact(0, *cnt_p);
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
         const unsigned int v = disk_hist[j];
