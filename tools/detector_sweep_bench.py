@@ -32,18 +32,20 @@ def pose(theta, phi, r):           # addDetectorDisk, integratingSphereDetectorS
 ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=100_000_000)
 ap.add_argument("--out", default="")
+ap.add_argument("--contract", default="exact", choices=["exact", "fast", "fast7"])
 a = ap.parse_args()
 poses = [pose(th, ph, 200.0) for th in np.arange(-45.0, 45.0 + 1e-9, 0.5) for ph in (0.0, 180.0)]
 centers = np.array([c for c, _ in poses]); rots = np.array([m for _, m in poses])
 sc = A.scene(theta_max=170.0, r_outer=105.0, world_half=200.0, reflectance=1.0, roughness=0.0, max_bounces=10000)
 src = A.source((-60.0, 0.0, -80.0), (1.0, 0.0, 0.0))
 with A.Context([0]) as ctx:
+    ctx.set_contract({"exact": A.CONTRACT_EXACT, "fast": A.CONTRACT_FAST, "fast7": A.CONTRACT_FAST7}[a.contract])
     ctx.detector_sweep(sc, src, 1_000_000, centers, rots)            # warm-up
     t0 = time.perf_counter()
     hits, st = ctx.detector_sweep(sc, src, a.rays, centers, rots)
     dt = time.perf_counter() - t0
 on_axis = [float(hits[i]) / a.rays for i, (c, _) in enumerate(poses) if abs(c[0]) < 1e-9 and abs(c[1]) < 1e-9]
-line = {"workload": "C4 integratingSphereDetectorSweep: trace once, 362 disk poses", "rays": a.rays, "poses": len(poses), "seconds": dt,
+line = {"workload": "C4 integratingSphereDetectorSweep: trace once, 362 disk poses", "contract": a.contract, "rays": a.rays, "poses": len(poses), "seconds": dt,
         "rays_per_s": a.rays / dt, "ray_bounces_per_s": st["n_bounces"] / dt, "bounces_per_ray": st["n_bounces"] / a.rays,
         "pose_tests_per_s": st["n_exited"] * len(poses) / dt, "on_axis_hit_fraction": on_axis,
         "reference_equivalent_rays": a.rays * len(poses)}

@@ -7,7 +7,7 @@ timeout 1500 python -m pytest tests -m gpu -q -x > $out/${tag}_pytest.log 2>&1; 
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$? ${SECONDS}s"
 timeout 600 python bench.py --map line --rays 100000000 --no-cpu > $out/${tag}_bench_line.json 2>> $out/${tag}_bench.err; echo "bench line rc=$? ${SECONDS}s"
-timeout 300 python tools/detector_sweep_bench.py > $out/${tag}_c4.json 2>> $out/${tag}_bench.err; echo "c4 rc=$? ${SECONDS}s"; cut -c60-140 $out/${tag}_c4.json
+for c in exact fast7; do timeout 300 python tools/detector_sweep_bench.py --contract $c > $out/${tag}_c4_$c.json 2>> $out/${tag}_bench.err; echo "c4 $c rc=$? ${SECONDS}s"; grep -o '"seconds": [0-9.]*' $out/${tag}_c4_$c.json; done
 python - <<PY
 import json
 for f in ('bench','bench_line'):
