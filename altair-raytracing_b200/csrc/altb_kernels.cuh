@@ -88,6 +88,11 @@ __device__ __forceinline__ int bounce_step(const Geom& g, const KConsts& k_, flo
         }
         dn = dot3(d, nrm);
     }
+    if (ALTB_FAST_FLIP_MIN && DEFER_CROSSING && ALTB_IS_FAST(C) && (MODEL != 0 || ROUGH)) {
+        // the same mirror without a condition: d - 2 min(d.n, 0) n (ptxas if-converts the branch into 8 predicated instructions)
+        d = axpy3(-2.0f * fminf(dn, 0.0f), nrm, d);
+        dn = fabsf(dn);
+    } else
     if ((MODEL != 0 || ROUGH) && dn < 0.0f) {      // keep the new direction on the incoming side of the TRUE surface
         d = axpy3(-2.0f * dn, nrm, d);
         dn = -dn;
