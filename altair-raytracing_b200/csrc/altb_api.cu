@@ -184,6 +184,9 @@ extern "C" void altb_destroy(altb_ctx* ctx) {
     delete ctx;
 }
 
+// k_trace's statistics buffer: [SMs][MAX_SLOTS][STAT_WORDS] block words, then [SMs][TRACE_THREADS][2] per-thread words (TraceParams::lane_acc)
+static inline size_t gstat_words(int sms) { return (size_t)sms * MAX_SLOTS * STAT_WORDS + (size_t)sms * TRACE_THREADS * 2; }
+
 extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
     if (!out) return fail(ALTB_E_ARG, "altb_create: out is NULL");
     *out = nullptr;
@@ -217,8 +220,8 @@ extern "C" int altb_create(altb_ctx** out, const int* devices, int n_devices) {
             cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&d.rq[0], (size_t)prop.multiProcessorCount * TRACE_WARPS * RQCAP * sizeof(QEntry)) != cudaSuccess ||
             cudaMalloc(&d.rq[1], (size_t)prop.multiProcessorCount * TRACE_WARPS * RQCAP * sizeof(QEntry)) != cudaSuccess ||
-            cudaMalloc(&d.gstat[0], (size_t)prop.multiProcessorCount * MAX_SLOTS * STAT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMalloc(&d.gstat[1], (size_t)prop.multiProcessorCount * MAX_SLOTS * STAT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.gstat[0], gstat_words(prop.multiProcessorCount) * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.gstat[1], gstat_words(prop.multiProcessorCount) * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&d.sincos, TABS_BYTES) != cudaSuccess) {
             const char* msg = cudaGetErrorString(cudaGetLastError());
             altb_destroy(ctx);
@@ -407,6 +410,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     P.ray_id0 = ray_id0; P.ctr_lo0 = (uint32_t)ray_id0; P.ctr_hi = (uint32_t)(ray_id0 >> 32);
     P.n = n;
     P.sincos = d.sincos; P.rq = rq; P.gstat = gstat;
+    P.lane_acc = gstat + (size_t)d.sm_count * MAX_SLOTS * STAT_WORDS;       // behind the block statistics, same allocation
     uint32_t sbits = 1;
     while ((1u << sbits) < P.n_slots) sbits++;
     P.shift = 32 - sbits; P.imask = (1u << P.shift) - 1u;
@@ -426,6 +430,8 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     P.n_chunks = P.cps * P.n_slots;
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     if (sink != SINK_RECORDS) CK(cudaMemsetAsync(gstat, 0, (size_t)blocks * P.n_slots * STAT_WORDS * sizeof(unsigned long long), st));
+    const bool lane_acc = ALTB_LANE_ACC && sink != SINK_RECORDS && P.n_slots == 1 && P.kind0 == EV_WALL;
+    if (lane_acc) CK(cudaMemsetAsync(P.lane_acc, 0, (size_t)blocks * TRACE_THREADS * 2 * sizeof(unsigned long long), st));
     cudaError_t le = cudaSuccess;
     if (P.kind0 != EV_WALL) {   // source aimed at the port rim: generic tracer (k_trace's fresh rays start on the sphere)
         if (sink != SINK_RECORDS || P.n_slots != 1) return fail(ALTB_E_ARG, "run_trace: rim-aimed sources go through the record path");
@@ -445,6 +451,7 @@ static int run_trace(altb_ctx* ctx, DevCtx& d, TraceSetup& ts, int sink, uint64_
     ctx->trace_launches++;
     CK(le);
     if (sink != SINK_RECORDS) {
+        if (lane_acc) { k_reduce_lane_acc<<<blocks, TRACE_THREADS, 0, st>>>(P); ctx->launches++; }
         k_reduce_trace_stats<<<(P.n_slots + 63) / 64, 64, 0, st>>>(P, blocks);
         ctx->launches++;
         CK(cudaGetLastError());

@@ -59,6 +59,7 @@ struct TraceParams {
     uint32_t n_slots, shift, imask, cps, n_chunks;
     QEntry* rq;           // resume queues in global memory: [grid * warps][RQCAP]
     unsigned long long* gstat;   // SINK_DIRECTION: per-block statistics [grid][n_slots][STAT_WORDS], zeroed before the launch
+    unsigned long long* lane_acc;  // single-slot direction / lines sink: per-THREAD (hits of ended rays, suspended rays) [grid][threads][2], zeroed before the launch
     // SINK_DIRECTION: the maps / statistics the kernel adds to, bins of the direction map
     unsigned long long* counts_base; unsigned long long* stats_base;
     uint32_t nb; int n_theta, n_phi;

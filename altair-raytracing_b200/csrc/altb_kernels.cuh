@@ -280,6 +280,9 @@ __device__ __forceinline__ bool line_rects(const RectParams& M, const f3& L, con
 #endif
 static constexpr int TRACE_THREADS = ALTB_TRACE_THREADS;
 static constexpr int TRACE_WARPS = TRACE_THREADS / 32;
+#ifndef ALTB_LANE_ACC
+#define ALTB_LANE_ACC 1      // 0: the warp-reduced RED.64 accounting of ended rays (experiment switch)
+#endif
 #ifndef ALTB_BOUNCES_PER_CHECK
 #define ALTB_BOUNCES_PER_CHECK 4
 #endif
@@ -479,7 +482,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
         if (need) {
             if (SINK == SINK_DIRECTION) {               // account for the rays that ended since the last check
                 const uint32_t hraw = alive ? 0u : s.hits;
-                if (!BATCHED) {
+                if (!BATCHED && ALTB_LANE_ACC) {
+                    // the lane's PRIVATE pair of words in global memory (hits of its ended rays, suspended rays): a plain
+                    // 128-bit read-modify-write, no atomics, no cross-lane reduction, nothing after the loop; k_reduce_lane_acc
+                    // sums them after the launch.  (REDUX + ballot + two warp-aggregated RED.64 by lane 0 were ~39 issue
+                    // slots per pass, 23 of them with one active lane.)
+                    if (hraw) {
+                        ulonglong2* a = reinterpret_cast<ulonglong2*>(P.lane_acc) + ((size_t)blockIdx.x * TRACE_THREADS + threadIdx.x);
+                        ulonglong2 v = *a;
+                        v.x += hraw & 0x7fffffffu; v.y += hraw >> 31;
+                        *a = v;
+                    }
+                } else if (!BATCHED) {
                     const uint32_t tot = __reduce_add_sync(FULL, hraw & 0x7fffffffu);
                     const uint32_t nsus = __popc(__ballot_sync(FULL, (hraw >> 31) != 0u));
                     if (ALTB_LANE == 0 && tot) {             // (no shared-memory accumulator + flush at the end: any code after
@@ -590,6 +604,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
 #undef ALTB_XQ
 #undef ALTB_RQ
 #undef ALTB_EXHAUSTED
+
+// single-slot direction / lines sink: the threads' private (hits, suspended) words -> their block's statistics words
+__global__ void __launch_bounds__(TRACE_THREADS) k_reduce_lane_acc(const __grid_constant__ TraceParams P) {
+    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(P.lane_acc)[(size_t)blockIdx.x * TRACE_THREADS + threadIdx.x];
+    unsigned long long h = v.x, s = v.y;
+    for (int o = 16; o; o >>= 1) { h += __shfl_xor_sync(FULL, h, o); s += __shfl_xor_sync(FULL, s, o); }
+    if ((threadIdx.x & 31u) == 0) {
+        unsigned long long* gs = trace_stats(P, 1u, 0u);
+        if (h) atomicAdd(gs + 4, h);
+        if (s) atomicAdd(gs + 3, s);
+    }
+}
 
 // SINK_DIRECTION: the blocks' private statistics -> the scenes' 8 statistics words
 // (n_rays, n_exited, n_exit_port, n_absorbed, n_suspended, n_bounces, 0, 0), added to.  One thread per slot.
