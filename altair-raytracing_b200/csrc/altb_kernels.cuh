@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 1) k_trace(const __grid_constan
 
     // SINK_DIRECTION: a ray that ends on the wall (absorbed / suspended) costs the bounce body NOTHING: the dead lane keeps its
     // hit count (bit 31 = suspended) and the next regeneration accounts for all dead lanes of the warp at full width --
-    // single scene: one REDUX + one ballot, lane 0 adds the warp's sums to the block's statistics (RED.64);
-    // batched: one RED.64 per ended ray into its slot.  Absorbed rays are not counted at all: absorbed = rays - exited -
+    // single scene: a predicated 128-bit read-modify-write of the lane's private (hits, suspended) words (TraceParams::lane_acc,
+    // summed by k_reduce_lane_acc after the launch); batched: one RED.64 per ended ray into its slot.  Absorbed rays are not counted at all: absorbed = rays - exited -
     // suspended (k_reduce_trace_stats).  (Done in the bounce body, ptxas if-converts the accounting: ~7 predicated
     // instructions per surface hit for an event that happens once per ray.)
 
