@@ -88,3 +88,8 @@ def test_hot_loop_has_no_spills(altb):
         want_f = {f"1,{m},{s}" for m in (0, 1) for s in (0, 1, 2, 3)}
         assert set(got) >= want_f, out
         assert all(got[k] <= 4 for k in want_f), (label, out)
+    # static length of one unrolled bounce body of the headline instance (CustomMirror + roughness, in-kernel direction map):
+    # the kernel is bound by issue slots, so this number IS the throughput (profiles/README.md: 185 -> 172 in the third
+    # session of round 2; exact contract 344)
+    body = {m.group(1): int(m.group(2)) for m in re.finditer(r"k_trace<1,1,1>( fast7| fast|):.*?, (\d+) per bounce body", out)}
+    assert body.get(" fast7", 999) <= 176 and body.get(" fast", 999) <= 192 and body.get("", 999) <= 350, body
