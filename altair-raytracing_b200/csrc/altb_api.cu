@@ -764,9 +764,26 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
     if (any_rec) if (int rc = ensure(d.rec, d.rec_cap, batch_rec)) return rc;
     const bool overlap = !t_trace_ms && dir_mode && n_launches >= 2 && !getenv("ALTB_NO_OVERLAP");
     LaunchSlot ls[2] = {{st, d.counter, d.rq[0], d.gstat[0], d.rec}, {st, d.counter2, d.rq[1], d.gstat[1], d.rec}};
+    // the worker streams are joined to the caller's stream on EVERY way out of this function once they are forked (the CK /
+    // ensure returns inside the launch loop included): work queued behind `st` must never overtake a launch still running
+    struct Join {
+        DevCtx& d; cudaStream_t st; bool armed;
+        cudaError_t run() {
+            cudaError_t first = cudaSuccess;
+            if (armed) for (int i = 0; i < 2; i++) {
+                cudaError_t e = cudaEventRecord(d.join_ev[i], d.aux[i]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, d.join_ev[i], 0);
+                if (e != cudaSuccess && first == cudaSuccess) first = e;
+            }
+            armed = false;
+            return first;
+        }
+        ~Join() { run(); }
+    } join{d, st, false};
     if (overlap) {
         if (any_rec) { if (int rc = ensure(d.rec2, d.rec2_cap, batch_rec)) return rc; ls[1].rec = d.rec2; }
         CK(cudaEventRecord(d.fork_ev, st));
+        join.armed = true;
         for (int i = 0; i < 2; i++) { CK(cudaStreamWaitEvent(d.aux[i], d.fork_ev, 0)); ls[i].st = d.aux[i]; }
     }
     uint64_t launch_no = 0;
@@ -827,12 +844,9 @@ static int fluxmap_on_device(altb_ctx* ctx, DevCtx& d, const altb_scene* scenes,
         // scenes that shared launches share their device time equally
         if (t_trace_ms) for (int sidx : g) { t_trace_ms[sidx] = tt / g.size(); t_map_ms[sidx] = tm / g.size(); }
     }
-    if (overlap) {                                      // join, also on the error path
-        for (int i = 0; i < 2; i++) {
-            cudaError_t e = cudaEventRecord(d.join_ev[i], d.aux[i]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, d.join_ev[i], 0);
-            if (e != cudaSuccess && !rc_all) rc_all = fail(ALTB_E_CUDA, "fluxmap: stream join failed: %s", cudaGetErrorString(e));
-        }
+    if (overlap) {                                      // join (the guard above does the same on the early returns)
+        const cudaError_t e = join.run();
+        if (e != cudaSuccess && !rc_all) rc_all = fail(ALTB_E_CUDA, "fluxmap: stream join failed: %s", cudaGetErrorString(e));
     }
     return rc_all;
 }
